@@ -1,0 +1,146 @@
+/*
+ * sqsm_b200.h — C ABI of libsqsm_b200.so, the B200-native (sm_100a) replacement for the
+ * `spconv-contraction` skeletonisation stage of project-lightlin/SmartQSM v2.1.3.
+ *
+ * The reference reaches this path through a Python plug-in class and un-vendored wheels
+ * (spconv, Open3D, SciPy); it has no FFI of its own.  The entry points below are what a
+ * ctypes binding of that plug-in binds; each one names the reference
+ * interface it replaces (paths relative to the reference checkout).
+ *
+ * Conventions: plain C, no torch types; `h_` pointers are HOST memory, `d_` pointers are
+ * DEVICE memory of the handle's GPU; sizes are element counts; every function returns 0 on
+ * success and a non-zero status otherwise, with a message available from
+ * sqsm_last_error().  A handle is not thread-safe and owns one CUDA stream; several handles
+ * (one per process / GPU) can coexist.  There is no CPU fallback: sqsm_create() fails when
+ * no sm_100 device is present.
+ */
+#ifndef SQSM_B200_H
+#define SQSM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sqsm_engine* sqsm_handle;
+
+/* core_algorithm_kwargs of configs/spconv-contraction-*.yaml:10-18 and the constructor
+ * SpconvBasedContraction.__init__ (core/core_algorithms/spconv_based_contraction.py:51-73). */
+typedef struct SqsmConfig {
+    int32_t device;                     /* CUDA device ordinal ("device: cuda")              */
+    int32_t batch_size;                 /* cubes per network batch (16)                       */
+    int32_t max_iteration;              /* informational; the caller drives the iterations    */
+    float   voxel_size;                 /* 0.01                                               */
+    float   cube_size;                  /* 4.0                                                */
+    float   buffer_size;                /* 0.4                                                */
+    int32_t monitored_by_chamfer_distance; /* 0/1                                             */
+    int32_t latch_early_stop;           /* 1: remember a Chamfer rejection (fixes F10; results
+                                           identical); 0: recompute like the reference does  */
+    int32_t down_kernel_flip;           /* 0: k index = (z&1,y&1,x&1) (SURVEY App. A default) */
+    int32_t reserved[7];
+} SqsmConfig;
+
+/* What one _contract() call did (spconv_based_contraction.py:75-140). */
+typedef struct SqsmIterStats {
+    int64_t n_in;                       /* points entering the iteration                      */
+    int64_t n_entries;                  /* sum over cube samples of points in the halo box    */
+    int64_t n_vox;                      /* level-0 voxels (network rows), all batches         */
+    int64_t n_rows_l1, n_rows_l2, n_rows_l3;
+    int64_t n_out;                      /* interior voxels = points leaving the iteration     */
+    int64_t n_cubes;
+    int64_t n_batches;
+    int64_t far_face_rows;              /* rows on the far faces of a batch box (App. D.3)    */
+    int64_t pairs_l0, pairs_l1, pairs_l2, pairs_l3; /* active SubM pairs incl. centre         */
+    double  chamfer;                    /* NaN when the monitor is off                         */
+    int32_t accepted;                   /* 1 = state replaced, 0 = rejected by the monitor    */
+    int32_t skipped;                    /* 1 = latched early stop, nothing computed            */
+    int32_t epoch;
+    int32_t gpu_launches;               /* kernels launched by this call                       */
+    float   ms_tiling, ms_voxel, ms_rulebook, ms_network, ms_chamfer; /* CUDA-event times       */
+} SqsmIterStats;
+
+/* ---- life cycle ------------------------------------------------------------------------ */
+int  sqsm_create(const SqsmConfig* cfg, sqsm_handle* out);
+void sqsm_destroy(sqsm_handle h);
+const char* sqsm_last_error(sqsm_handle h);      /* h may be NULL: error of a failed create  */
+int  sqsm_abi_version(void);
+
+/* Weights: the reference loads `ckpt["model_state_dict"]` into SmartTreeXX
+ * (spconv_based_contraction.py:62-69).  Tensors are passed one by one by their state-dict
+ * name, float32, C-contiguous, original layout ([C_out,kz,ky,kx,C_in] for
+ * convolutions, [out,in] for nn.Linear).  sqsm_finalize_weights() folds BatchNorm(eps=1e-4)
+ * running statistics and uploads everything; it fails if a tensor is missing. */
+int  sqsm_set_weight(sqsm_handle h, const char* name, const float* h_data, int64_t n_elem);
+int  sqsm_finalize_weights(sqsm_handle h);
+
+/* ---- the plug-in path ------------------------------------------------------------------ */
+/* CoreAlgorithmBase.input(points=...) (core/core_algorithms/core_algorithm_base.py:31-34):
+ * N x 3 float64, host (copied, cast to float32 like spconv_based_contraction.py:82) or
+ * already on the device as float32 (device-resident variant used for kernel-only timing).
+ * Resets epoch, displacements and the Chamfer state. */
+int  sqsm_set_points_f64(sqsm_handle h, const double* h_xyz, int64_t n);
+int  sqsm_set_points_dev_f32(sqsm_handle h, const float* d_xyz, int64_t n);
+/* Resume from a saved state: float32 contracted points AND accumulated displacements (host),
+ * i.e. the two arrays of SpconvBasedContraction.output() (:147-151).  Epoch restarts at 0. */
+int  sqsm_set_state_f32(sqsm_handle h, const float* h_xyz, const float* h_disp, int64_t n);
+
+/* One thunk of get_pipeline() = one SpconvBasedContraction._contract()
+ * (spconv_based_contraction.py:75-140).  `stats` may be NULL. */
+int  sqsm_contract_step(sqsm_handle h, SqsmIterStats* stats);
+
+/* SpconvBasedContraction.output() (spconv_based_contraction.py:147-151): sizes, then copy. */
+int  sqsm_result_size(sqsm_handle h, int64_t* n);
+int  sqsm_get_result(sqsm_handle h, float* h_contracted_xyz, float* h_displacements_xyz);
+
+/* ThinningBasedSkeletonizationPipeline._produce_skeletal_points_and_radii
+ * (core/thinning_based_skeletonization_pipeline.py:68-80) on the current state: one point
+ * per `voxel` cell (lowest original index), radii = ||displacement||.  Node numbering =
+ * ascending sample id.  Call with NULL outputs to obtain *m only. */
+int  sqsm_skeletal_sample(sqsm_handle h, double voxel, int64_t* m,
+                          int64_t* h_sample_ids, float* h_points_xyz, float* h_radii);
+
+/* Radius-neighbour edge set of SkeletonizationPipelineBase._construct_graph
+ * (core/skeletonization_pipeline_base.py:132-144, merged and sorted at :158) over the
+ * skeletal points of the last sqsm_skeletal_sample(): all i<j with ||p_i-p_j|| <= r
+ * (float64 test), lexicographic.  Call with h_edges == NULL to obtain *n_edges only. */
+int  sqsm_radius_graph(sqsm_handle h, double r, int64_t* n_edges, int64_t* h_edges_ij);
+
+/* Same operator on caller-provided points (host float32 M x 3), independent of the state. */
+int  sqsm_radius_graph_points(sqsm_handle h, const float* h_points_xyz, int64_t m, double r,
+                              int64_t* n_edges, int64_t* h_edges_ij, int64_t capacity);
+
+/* ---- parity / inspection hooks (integer outputs of the LAST sqsm_contract_step) --------
+ * Rows are reported in CANONICAL order: by cube sample, then ascending
+ * winning point index.  Enable capture before the step; it keeps the per-level tables. */
+int  sqsm_debug_capture(sqsm_handle h, int32_t enable);
+int  sqsm_debug_level_size(sqsm_handle h, int32_t level, int64_t* n_rows);
+/* level 0: indices = (sample, z, y, x) int32[n,4]; winner = input row int64[n]; mask uint8[n];
+ * batch spatial_shape (max index z,y,x) int32[n_batches,3] via sqsm_debug_batch_shapes. */
+int  sqsm_debug_voxels(sqsm_handle h, int32_t* h_indices, int64_t* h_winner, uint8_t* h_mask);
+int  sqsm_debug_batch_shapes(sqsm_handle h, int32_t* h_shapes_zyx, int32_t* h_descend_flags);
+/* per level: coordinates (sample, z, y, x) of every row in internal order, SubM table
+ * nbr[27][n] (internal row numbers, -1 = none) and, for levels < 3, parent[n] / koff[n]. */
+int  sqsm_debug_level_tables(sqsm_handle h, int32_t level, int32_t* h_coords, int32_t* h_nbr,
+                             int32_t* h_parent, int32_t* h_koff);
+/* level-0 permutation: canonical row -> internal row. */
+int  sqsm_debug_canon_to_internal(sqsm_handle h, int32_t* h_perm);
+/* network outputs per level-0 row, internal order: direction*distance float32[n,3], plus the
+ * raw heads offset[n,3], regression[n] */
+int  sqsm_debug_predictions(sqsm_handle h, float* h_pred, float* h_offset, float* h_regression);
+/* activations after a named stage, internal row order of `level`; float32[n, channels] */
+int  sqsm_debug_features(sqsm_handle h, const char* stage, int32_t* level, int32_t* channels,
+                         float* h_data, int64_t capacity);
+
+/* ---- measurement hooks ------------------------------------------------------------------ */
+/* device-time (CUDA events on the handle's stream) and launch count of one named kernel
+ * family accumulated since the last reset; used by bench.py for roofline.achieved. */
+int  sqsm_profile_reset(sqsm_handle h);
+int  sqsm_profile_get(sqsm_handle h, const char* family, double* total_ms, int64_t* launches,
+                      double* algorithmic_bytes);
+int  sqsm_profile_enable(sqsm_handle h, int32_t enable);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQSM_B200_H */

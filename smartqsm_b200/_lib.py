@@ -1,0 +1,294 @@
+"""ctypes binding of ``libsqsm_b200.so`` (C ABI in ``include/sqsm_b200.h``).
+
+There is no CPU fallback: importing this module without the built library raises, and
+``Engine`` raises when no sm_100 GPU is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsqsm_b200.so")
+
+
+class SqsmConfig(C.Structure):
+    _fields_ = [
+        ("device", C.c_int32), ("batch_size", C.c_int32), ("max_iteration", C.c_int32),
+        ("voxel_size", C.c_float), ("cube_size", C.c_float), ("buffer_size", C.c_float),
+        ("monitored_by_chamfer_distance", C.c_int32), ("latch_early_stop", C.c_int32),
+        ("down_kernel_flip", C.c_int32), ("reserved", C.c_int32 * 7),
+    ]
+
+
+class SqsmIterStats(C.Structure):
+    _fields_ = [
+        ("n_in", C.c_int64), ("n_entries", C.c_int64), ("n_vox", C.c_int64),
+        ("n_rows_l1", C.c_int64), ("n_rows_l2", C.c_int64), ("n_rows_l3", C.c_int64),
+        ("n_out", C.c_int64), ("n_cubes", C.c_int64), ("n_batches", C.c_int64), ("far_face_rows", C.c_int64),
+        ("pairs_l0", C.c_int64), ("pairs_l1", C.c_int64), ("pairs_l2", C.c_int64), ("pairs_l3", C.c_int64),
+        ("chamfer", C.c_double), ("accepted", C.c_int32), ("skipped", C.c_int32), ("epoch", C.c_int32),
+        ("gpu_launches", C.c_int32),
+        ("ms_tiling", C.c_float), ("ms_voxel", C.c_float), ("ms_rulebook", C.c_float), ("ms_network", C.c_float),
+        ("ms_chamfer", C.c_float),
+    ]
+
+    def as_dict(self) -> dict:
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTS = [
+    "sqsm_create", "sqsm_destroy", "sqsm_last_error", "sqsm_abi_version", "sqsm_set_weight",
+    "sqsm_finalize_weights", "sqsm_set_points_f64", "sqsm_set_points_dev_f32", "sqsm_set_state_f32", "sqsm_contract_step",
+    "sqsm_result_size", "sqsm_get_result", "sqsm_skeletal_sample", "sqsm_radius_graph",
+    "sqsm_radius_graph_points", "sqsm_debug_capture", "sqsm_debug_level_size", "sqsm_debug_voxels",
+    "sqsm_debug_batch_shapes", "sqsm_debug_level_tables", "sqsm_debug_canon_to_internal",
+    "sqsm_debug_predictions", "sqsm_debug_features", "sqsm_profile_reset", "sqsm_profile_get",
+    "sqsm_profile_enable",
+]
+
+_lib: Optional[C.CDLL] = None
+
+
+def load_library() -> C.CDLL:
+    """Load the CUDA library; raise loudly if it was never built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m smartqsm_b200.build` (nvcc, sm_100a). "
+            "smartqsm_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, cp, i64, i32, f64 = C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, C.c_double
+    P = C.POINTER
+    sig = {
+        "sqsm_create": ([P(SqsmConfig), P(vp)], C.c_int),
+        "sqsm_destroy": ([vp], None),
+        "sqsm_last_error": ([vp], cp),
+        "sqsm_abi_version": ([], C.c_int),
+        "sqsm_set_weight": ([vp, cp, vp, i64], C.c_int),
+        "sqsm_finalize_weights": ([vp], C.c_int),
+        "sqsm_set_points_f64": ([vp, vp, i64], C.c_int),
+        "sqsm_set_points_dev_f32": ([vp, vp, i64], C.c_int),
+        "sqsm_set_state_f32": ([vp, vp, vp, i64], C.c_int),
+        "sqsm_contract_step": ([vp, P(SqsmIterStats)], C.c_int),
+        "sqsm_result_size": ([vp, P(i64)], C.c_int),
+        "sqsm_get_result": ([vp, vp, vp], C.c_int),
+        "sqsm_skeletal_sample": ([vp, f64, P(i64), vp, vp, vp], C.c_int),
+        "sqsm_radius_graph": ([vp, f64, P(i64), vp], C.c_int),
+        "sqsm_radius_graph_points": ([vp, vp, i64, f64, P(i64), vp, i64], C.c_int),
+        "sqsm_debug_capture": ([vp, i32], C.c_int),
+        "sqsm_debug_level_size": ([vp, i32, P(i64)], C.c_int),
+        "sqsm_debug_voxels": ([vp, vp, vp, vp], C.c_int),
+        "sqsm_debug_batch_shapes": ([vp, vp, vp], C.c_int),
+        "sqsm_debug_level_tables": ([vp, i32, vp, vp, vp, vp], C.c_int),
+        "sqsm_debug_canon_to_internal": ([vp, vp], C.c_int),
+        "sqsm_debug_predictions": ([vp, vp, vp, vp], C.c_int),
+        "sqsm_debug_features": ([vp, cp, P(i32), P(i32), vp, i64], C.c_int),
+        "sqsm_profile_reset": ([vp], C.c_int),
+        "sqsm_profile_get": ([vp, cp, P(f64), P(i64), P(f64)], C.c_int),
+        "sqsm_profile_enable": ([vp, i32], C.c_int),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = args, res
+    _lib = lib
+    return lib
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """Thin object wrapper over one ``sqsm_handle``."""
+
+    def __init__(self, *, device: int = 0, batch_size: int = 16, max_iteration: int = 10, voxel_size: float = 0.01,
+                 cube_size: float = 4.0, buffer_size: float = 0.4, monitored_by_chamfer_distance: bool = False,
+                 latch_early_stop: bool = False, down_kernel_flip: bool = False) -> None:
+        self._lib = load_library()
+        cfg = SqsmConfig(device=device, batch_size=batch_size, max_iteration=max_iteration, voxel_size=voxel_size,
+                         cube_size=cube_size, buffer_size=buffer_size,
+                         monitored_by_chamfer_distance=int(monitored_by_chamfer_distance),
+                         latch_early_stop=int(latch_early_stop), down_kernel_flip=int(down_kernel_flip))
+        h = C.c_void_p()
+        rc = self._lib.sqsm_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise RuntimeError("sqsm_create failed: " + self._lib.sqsm_last_error(None).decode())
+        self._h = h
+        self._keepalive = None
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.sqsm_destroy(self._h)
+            self._h = None
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            raise RuntimeError(f"{what} failed: " + self._lib.sqsm_last_error(self._h).decode())
+
+    # ---- weights
+    def load_state_dict(self, state: Dict[str, np.ndarray]) -> None:
+        for name, v in state.items():
+            if name.endswith("num_batches_tracked"):
+                continue
+            a = np.ascontiguousarray(np.asarray(v), dtype=np.float32)
+            self._check(self._lib.sqsm_set_weight(self._h, name.encode(), _ptr(a), a.size), f"set_weight({name})")
+        self._check(self._lib.sqsm_finalize_weights(self._h), "finalize_weights")
+
+    # ---- plug-in path
+    def set_points(self, points: np.ndarray) -> None:
+        a = np.ascontiguousarray(points, dtype=np.float64)
+        assert a.ndim == 2 and a.shape[1] == 3
+        self._check(self._lib.sqsm_set_points_f64(self._h, _ptr(a), a.shape[0]), "set_points")
+
+    def set_points_ptr_f64(self, host_ptr: int, n: int) -> None:
+        self._check(self._lib.sqsm_set_points_f64(self._h, C.c_void_p(host_ptr), n), "set_points")
+
+    def set_points_device_f32(self, dev_ptr: int, n: int) -> None:
+        self._check(self._lib.sqsm_set_points_dev_f32(self._h, C.c_void_p(dev_ptr), n), "set_points_dev")
+
+    def set_state(self, points_f32: np.ndarray, disp_f32: np.ndarray) -> None:
+        p = np.ascontiguousarray(points_f32, dtype=np.float32)
+        d = np.ascontiguousarray(disp_f32, dtype=np.float32)
+        assert p.shape == d.shape and p.ndim == 2 and p.shape[1] == 3
+        self._check(self._lib.sqsm_set_state_f32(self._h, _ptr(p), _ptr(d), p.shape[0]), "set_state")
+
+    def contract_step(self) -> dict:
+        st = SqsmIterStats()
+        self._check(self._lib.sqsm_contract_step(self._h, C.byref(st)), "contract_step")
+        return st.as_dict()
+
+    def result(self) -> Tuple[np.ndarray, np.ndarray]:
+        n = C.c_int64()
+        self._check(self._lib.sqsm_result_size(self._h, C.byref(n)), "result_size")
+        p = np.empty((n.value, 3), np.float32)
+        d = np.empty((n.value, 3), np.float32)
+        self._check(self._lib.sqsm_get_result(self._h, _ptr(p), _ptr(d)), "get_result")
+        return p, d
+
+    def result_into(self, p_ptr: int, d_ptr: int) -> int:
+        n = C.c_int64()
+        self._check(self._lib.sqsm_result_size(self._h, C.byref(n)), "result_size")
+        self._check(self._lib.sqsm_get_result(self._h, C.c_void_p(p_ptr), C.c_void_p(d_ptr)), "get_result")
+        return n.value
+
+    def result_size(self) -> int:
+        n = C.c_int64()
+        self._check(self._lib.sqsm_result_size(self._h, C.byref(n)), "result_size")
+        return n.value
+
+    def skeletal_sample(self, voxel: float = 0.01, fetch: bool = True):
+        m = C.c_int64()
+        self._check(self._lib.sqsm_skeletal_sample(self._h, voxel, C.byref(m), None, None, None), "skeletal_sample")
+        if not fetch:
+            return m.value
+        ids = np.empty(m.value, np.int64)
+        pts = np.empty((m.value, 3), np.float32)
+        rad = np.empty(m.value, np.float32)
+        self._check(self._lib.sqsm_skeletal_sample(self._h, voxel, C.byref(m), _ptr(ids), _ptr(pts), _ptr(rad)),
+                    "skeletal_sample")
+        return ids, pts, rad
+
+    def radius_graph(self, r: float = 0.055, fetch: bool = True):
+        """Edges over the last skeletal sample (computed once per sample and radius on the device;
+        ``fetch=False`` returns the count and leaves the edge list in HBM)."""
+        e = C.c_int64()
+        self._check(self._lib.sqsm_radius_graph(self._h, r, C.byref(e), None), "radius_graph")
+        if not fetch:
+            return e.value
+        out = np.empty((e.value, 2), np.int64)
+        if e.value:
+            self._check(self._lib.sqsm_radius_graph(self._h, r, C.byref(e), _ptr(out)), "radius_graph")
+        return out
+
+    def radius_graph_points(self, pts: np.ndarray, r: float) -> np.ndarray:
+        a = np.ascontiguousarray(pts, dtype=np.float32)
+        e = C.c_int64()
+        self._check(self._lib.sqsm_radius_graph_points(self._h, _ptr(a), a.shape[0], r, C.byref(e), None, 0),
+                    "radius_graph_points")
+        out = np.empty((e.value, 2), np.int64)
+        if e.value:
+            self._check(self._lib.sqsm_radius_graph_points(self._h, _ptr(a), a.shape[0], r, C.byref(e), _ptr(out),
+                                                           e.value), "radius_graph_points")
+        return out
+
+    # ---- inspection hooks
+    def debug_capture(self, enable: bool = True) -> None:
+        self._check(self._lib.sqsm_debug_capture(self._h, int(enable)), "debug_capture")
+
+    def debug_level_size(self, level: int) -> int:
+        n = C.c_int64()
+        self._check(self._lib.sqsm_debug_level_size(self._h, level, C.byref(n)), "debug_level_size")
+        return n.value
+
+    def debug_voxels(self):
+        n = self.debug_level_size(0)
+        idx = np.empty((n, 4), np.int32)
+        win = np.empty(n, np.int64)
+        mask = np.empty(n, np.uint8)
+        self._check(self._lib.sqsm_debug_voxels(self._h, _ptr(idx), _ptr(win), _ptr(mask)), "debug_voxels")
+        return idx, win, mask.astype(bool)
+
+    def debug_batch_shapes(self, n_batches: int):
+        shp = np.empty((n_batches, 3), np.int32)
+        desc = np.empty((3, n_batches), np.int32)
+        self._check(self._lib.sqsm_debug_batch_shapes(self._h, _ptr(shp), _ptr(desc)), "debug_batch_shapes")
+        return shp, desc
+
+    def debug_level_tables(self, level: int, with_down: bool):
+        n = self.debug_level_size(level)
+        coords = np.empty((n, 4), np.int32)
+        nbr = np.empty((27, n), np.int32)
+        parent = np.empty(n, np.int32) if with_down else None
+        koff = np.empty(n, np.int32) if with_down else None
+        self._check(self._lib.sqsm_debug_level_tables(self._h, level, _ptr(coords), _ptr(nbr), _ptr(parent), _ptr(koff)),
+                    "debug_level_tables")
+        return coords, nbr, parent, koff
+
+    def debug_canon_to_internal(self) -> np.ndarray:
+        n = self.debug_level_size(0)
+        perm = np.empty(n, np.int32)
+        self._check(self._lib.sqsm_debug_canon_to_internal(self._h, _ptr(perm)), "debug_canon_to_internal")
+        return perm
+
+    def debug_predictions(self):
+        n = self.debug_level_size(0)
+        pred = np.empty((n, 3), np.float32)
+        off = np.empty((n, 3), np.float32)
+        reg = np.empty(n, np.float32)
+        self._check(self._lib.sqsm_debug_predictions(self._h, _ptr(pred), _ptr(off), _ptr(reg)), "debug_predictions")
+        return pred, off, reg
+
+    def debug_features(self, stage: str) -> Tuple[np.ndarray, int]:
+        lvl, ch = C.c_int32(), C.c_int32()
+        self._check(self._lib.sqsm_debug_features(self._h, stage.encode(), C.byref(lvl), C.byref(ch), None, 0),
+                    "debug_features")
+        n = self.debug_level_size(lvl.value)
+        out = np.empty((n, ch.value), np.float32)
+        self._check(self._lib.sqsm_debug_features(self._h, stage.encode(), C.byref(lvl), C.byref(ch), _ptr(out), out.size),
+                    "debug_features")
+        return out, lvl.value
+
+    # ---- measurement hooks
+    def profile_enable(self, enable: bool = True) -> None:
+        self._check(self._lib.sqsm_profile_enable(self._h, int(enable)), "profile_enable")
+
+    def profile_reset(self) -> None:
+        self._check(self._lib.sqsm_profile_reset(self._h), "profile_reset")
+
+    def profile_get(self, family: str):
+        ms, n, by = C.c_double(), C.c_int64(), C.c_double()
+        self._check(self._lib.sqsm_profile_get(self._h, family.encode(), C.byref(ms), C.byref(n), C.byref(by)),
+                    "profile_get")
+        return ms.value, n.value, by.value

@@ -1,0 +1,214 @@
+// BrickMap construction kernels (see brickmap.h).  sm_100a.
+#include "brickmap.h"
+#include <cub/cub.cuh>
+
+namespace sqsm {
+
+// ------------------------------------------------------------------ scan / sort wrappers (CUB)
+
+void exclusive_scan_i32(Ctx& cx, const int32_t* d_in, int32_t* d_out, int64_t n) {
+    if (n <= 0) return;
+    size_t tb = 0;
+    SQSM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_in, d_out, (int)n, cx.st));
+    DBuf<uint8_t> tmp((int64_t)tb + 16, cx.st);
+    SQSM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, d_in, d_out, (int)n, cx.st));
+    cx.launches += 2;
+}
+
+void exclusive_scan_i64(Ctx& cx, const int64_t* d_in, int64_t* d_out, int64_t n) {
+    if (n <= 0) return;
+    size_t tb = 0;
+    SQSM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_in, d_out, (int)n, cx.st));
+    DBuf<uint8_t> tmp((int64_t)tb + 16, cx.st);
+    SQSM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, d_in, d_out, (int)n, cx.st));
+    cx.launches += 2;
+}
+
+void sort_keys_u64(Ctx& cx, const uint64_t* d_in, uint64_t* d_out, int64_t n, int begin_bit, int end_bit) {
+    if (n <= 0) return;
+    size_t tb = 0;
+    SQSM_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, d_in, d_out, (int)n, begin_bit, end_bit, cx.st));
+    DBuf<uint8_t> tmp((int64_t)tb + 16, cx.st);
+    SQSM_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, d_in, d_out, (int)n, begin_bit, end_bit, cx.st));
+    cx.launches += 2 * ((end_bit - begin_bit + 7) / 8) + 1;
+}
+
+void sort_pairs_u32(Ctx& cx, const uint32_t* d_kin, uint32_t* d_kout, const uint32_t* d_vin, uint32_t* d_vout,
+                    int64_t n, int begin_bit, int end_bit) {
+    if (n <= 0) return;
+    size_t tb = 0;
+    SQSM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, d_kin, d_kout, d_vin, d_vout, (int)n, begin_bit,
+                                              end_bit, cx.st));
+    DBuf<uint8_t> tmp((int64_t)tb + 16, cx.st);
+    SQSM_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, d_kin, d_kout, d_vin, d_vout, (int)n, begin_bit,
+                                              end_bit, cx.st));
+    cx.launches += 2 * ((end_bit - begin_bit + 7) / 8) + 1;
+}
+
+// ------------------------------------------------------------------ kernels
+
+// Insert every entry's brick key; the thread that claims a slot appends the key to the list.
+__global__ void __launch_bounds__(256) k_brick_insert(BrickHash h, const uint64_t* __restrict__ ent_key,
+                                                      int64_t n_ent, uint64_t* __restrict__ list,
+                                                      int32_t* __restrict__ counter) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_ent) return;
+    uint64_t key = ent_key[e];
+    if (key == kEmptyKey) return;
+    // consecutive entries often fall in the same brick: let one lane per distinct key probe
+    unsigned peers = __match_any_sync(__activemask(), key);
+    if ((int)(__ffs(peers) - 1) != (int)(threadIdx.x & 31)) return;
+    bool ins;
+    hash_insert(h, key, &ins);
+    if (ins) list[atomicAdd(counter, 1)] = key;
+}
+
+// Brick i takes the i-th sorted key; publish the id in the hash.
+__global__ void __launch_bounds__(256) k_brick_init(BrickHash h, const uint64_t* __restrict__ sorted,
+                                                    int n_bricks, Brick* __restrict__ bricks) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_bricks) return;
+    uint64_t key = sorted[i];
+    bricks[i].key = key;
+    uint32_t slot = (uint32_t)mix64(key) & h.cap_mask;
+    while (h.keys[slot] != key) slot = (slot + 1) & h.cap_mask;
+    h.vals[slot] = i;
+}
+
+__global__ void __launch_bounds__(256) k_brick_setbits(BrickHash h, const uint64_t* __restrict__ ent_key,
+                                                       const uint16_t* __restrict__ ent_pos, int64_t n_ent,
+                                                       Brick* __restrict__ bricks, int32_t* __restrict__ ent_brick) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_ent) return;
+    uint64_t key = ent_key[e];
+    if (key == kEmptyKey) { ent_brick[e] = -1; return; }
+    int b = hash_find(h, key);
+    ent_brick[e] = b;
+    uint32_t pos = ent_pos[e];
+    atomicOr(&bricks[b].mask[pos >> 5], 1u << (pos & 31u));
+}
+
+// 16 lanes per brick: popcount per word, exclusive prefix inside the half warp.
+__global__ void __launch_bounds__(256) k_brick_prefix(Brick* __restrict__ bricks, int n_bricks,
+                                                      int32_t* __restrict__ counts) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = t >> 4, w = t & 15;
+    bool live = b < n_bricks;
+    uint32_t m = live ? bricks[b].mask[w] : 0u;
+    int c = __popc(m);
+    int incl = c;
+    #pragma unroll
+    for (int d = 1; d < 16; d <<= 1) {
+        int v = __shfl_up_sync(0xFFFFFFFFu, incl, d, 16);
+        if (w >= d) incl += v;
+    }
+    if (!live) return;
+    bricks[b].prefix[w] = (uint16_t)(incl - c);
+    if (w == 15) { bricks[b].count = incl; counts[b] = incl; }
+}
+
+__global__ void __launch_bounds__(256) k_brick_setbase(Brick* __restrict__ bricks, int n_bricks,
+                                                       const int32_t* __restrict__ base) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_bricks) bricks[i].base = base[i];
+}
+
+__global__ void __launch_bounds__(256) k_brick_neighbours(BrickHash h, const Brick* __restrict__ bricks,
+                                                          int n_bricks, int32_t* __restrict__ bnbr) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = t >> 5, j = t & 31;
+    if (b >= n_bricks) return;
+    int id = -1;
+    if (j < 27) {
+        uint64_t key = bricks[b].key;
+        int z = (int)key_z(key) + j / 9 - 1, y = (int)key_y(key) + (j / 3) % 3 - 1, x = (int)key_x(key) + j % 3 - 1;
+        if (j == 13) id = b;
+        else if (z >= 0 && y >= 0 && x >= 0 && z < 65536 && y < 65536 && x < 65536)
+            id = hash_find(h, pack_key(key_s(key), (uint32_t)z, (uint32_t)y, (uint32_t)x));
+    }
+    bnbr[(size_t)b * 32 + j] = id;
+}
+
+__global__ void __launch_bounds__(256) k_brick_expand(const Brick* __restrict__ bricks, int n_bricks,
+                                                      int32_t* __restrict__ row_brick, uint16_t* __restrict__ row_pos) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = t >> 4, w = t & 15;
+    if (b >= n_bricks) return;
+    uint32_t m = bricks[b].mask[w];
+    int row = bricks[b].base + (int)bricks[b].prefix[w];
+    while (m) {
+        int bit = __ffs(m) - 1;
+        m &= m - 1;
+        row_brick[row] = b;
+        row_pos[row] = (uint16_t)((w << 5) | bit);
+        ++row;
+    }
+}
+
+// ------------------------------------------------------------------ host side
+
+static uint32_t next_pow2(uint64_t v) {
+    uint64_t p = 1024;
+    while (p < v) p <<= 1;
+    SQSM_CHECK(p <= (1ull << 31), "brick hash too large");
+    return (uint32_t)p;
+}
+
+void brickmap_build(Ctx& cx, BrickMap& m, const uint64_t* d_ent_key, const uint16_t* d_ent_pos, int64_t n_ent,
+                    int32_t* d_ent_brick) {
+    cudaStream_t st = cx.st;
+    SQSM_CHECK(n_ent < (1ll << 31), "too many entries for one BrickMap build");
+    m.n_bricks = 0;
+    m.n_rows = 0;
+    if (n_ent == 0) return;
+    // <= 50 % load even if every entry opened its own brick
+    m.cap = next_pow2((uint64_t)n_ent * 2);
+    m.hkeys.alloc(m.cap, st);
+    m.hvals.alloc(m.cap, st);
+    m.hkeys.fill_ff();
+    DBuf<uint64_t> list(n_ent, st);
+    DBuf<int32_t> counter(1, st);
+    counter.zero();
+    int grid = div_up(n_ent, 256);
+    k_brick_insert<<<grid, 256, 0, st>>>(m.view(), d_ent_key, n_ent, list.p, counter.p);
+    cx.launches++;
+    int32_t nb = 0;
+    SQSM_CUDA(cudaMemcpyAsync(&nb, counter.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SQSM_CUDA(cudaStreamSynchronize(st));
+    m.n_bricks = nb;
+    if (nb == 0) return;
+    DBuf<uint64_t> sorted(nb, st);
+    sort_keys_u64(cx, list.p, sorted.p, nb, 0, 64);
+    m.bricks.alloc(nb, st);
+    m.bricks.zero();
+    k_brick_init<<<div_up(nb, 256), 256, 0, st>>>(m.view(), sorted.p, nb, m.bricks.p);
+    k_brick_setbits<<<grid, 256, 0, st>>>(m.view(), d_ent_key, d_ent_pos, n_ent, m.bricks.p, d_ent_brick);
+    DBuf<int32_t> counts((int64_t)nb + 1, st);
+    DBuf<int32_t> base((int64_t)nb + 1, st);
+    counts.zero();
+    k_brick_prefix<<<div_up((int64_t)nb * 16, 256), 256, 0, st>>>(m.bricks.p, nb, counts.p);
+    exclusive_scan_i32(cx, counts.p, base.p, (int64_t)nb + 1);
+    k_brick_setbase<<<div_up(nb, 256), 256, 0, st>>>(m.bricks.p, nb, base.p);
+    cx.launches += 4;
+    int32_t total = 0;
+    SQSM_CUDA(cudaMemcpyAsync(&total, base.p + nb, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SQSM_CUDA(cudaStreamSynchronize(st));
+    m.n_rows = total;
+}
+
+void brickmap_build_neighbours(Ctx& cx, BrickMap& m) {
+    if (m.n_bricks == 0) return;
+    m.bnbr.alloc((int64_t)m.n_bricks * 32, cx.st);
+    k_brick_neighbours<<<div_up((int64_t)m.n_bricks * 32, 256), 256, 0, cx.st>>>(m.view(), m.bricks.p, m.n_bricks,
+                                                                                m.bnbr.p);
+    cx.launches++;
+}
+
+void brickmap_expand_rows(Ctx& cx, const BrickMap& m, int32_t* d_row_brick, uint16_t* d_row_pos) {
+    if (m.n_bricks == 0) return;
+    k_brick_expand<<<div_up((int64_t)m.n_bricks * 16, 256), 256, 0, cx.st>>>(m.bricks.p, m.n_bricks, d_row_brick,
+                                                                             d_row_pos);
+    cx.launches++;
+}
+
+}  // namespace sqsm

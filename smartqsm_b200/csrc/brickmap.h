@@ -1,0 +1,53 @@
+// BrickMap: the coordinate structure behind voxelisation, rulebooks, the Chamfer monitor,
+// skeletal sampling and the radius graph.
+//
+// Two levels: an open-addressing hash (linear probing, 64-bit keys, <= 50 % load) maps the
+// coordinates of an 8x8x8-voxel brick to a brick id; a brick is one 128-byte line holding a
+// 512-bit occupancy bitmap plus popcount prefixes, so "is voxel v active and what is its
+// row" is one hash probe per brick and a popcount.  Bricks are numbered in sorted key order
+// (sample, bz, by, bx) and rows follow brick order, then (z, y, x) inside the brick, so rows
+// that are neighbours in space are neighbours in memory and the gathers of the sparse
+// convolutions hit L2.
+#pragma once
+#include "common.cuh"
+
+namespace sqsm {
+
+struct Ctx {                       // per-engine launch context
+    cudaStream_t st = nullptr;
+    int64_t launches = 0;
+};
+
+struct BrickMap {
+    DBuf<uint64_t> hkeys;
+    DBuf<int32_t>  hvals;
+    uint32_t cap = 0;
+    DBuf<Brick> bricks;
+    DBuf<int32_t> bnbr;            // [n_bricks][32]: ids of the 27 neighbour bricks (-1 = none)
+    int n_bricks = 0;
+    int64_t n_rows = 0;
+#ifdef __CUDACC__
+    BrickHash view() const { return BrickHash{hkeys.p, hvals.p, cap - 1}; }
+#endif
+};
+
+// Build a BrickMap from entries (brick key, position in brick).  Entries whose key is
+// kEmptyKey are ignored.  On return ent_brick[e] holds the brick id of every valid entry.
+// Synchronises the stream twice (brick count, row count).
+void brickmap_build(Ctx& cx, BrickMap& m, const uint64_t* d_ent_key, const uint16_t* d_ent_pos,
+                    int64_t n_ent, int32_t* d_ent_brick);
+
+// bnbr table (27 neighbour brick ids per brick); needed by the rulebook / NN / graph kernels.
+void brickmap_build_neighbours(Ctx& cx, BrickMap& m);
+
+// row -> (brick id, position) expansion; arrays sized n_rows.
+void brickmap_expand_rows(Ctx& cx, const BrickMap& m, int32_t* d_row_brick, uint16_t* d_row_pos);
+
+// small utilities shared by the translation units
+void exclusive_scan_i32(Ctx& cx, const int32_t* d_in, int32_t* d_out, int64_t n);   // out has n elements
+void exclusive_scan_i64(Ctx& cx, const int64_t* d_in, int64_t* d_out, int64_t n);
+void sort_keys_u64(Ctx& cx, const uint64_t* d_in, uint64_t* d_out, int64_t n, int begin_bit, int end_bit);
+void sort_pairs_u32(Ctx& cx, const uint32_t* d_kin, uint32_t* d_kout, const uint32_t* d_vin, uint32_t* d_vout,
+                    int64_t n, int begin_bit, int end_bit);
+
+}  // namespace sqsm

@@ -1,0 +1,549 @@
+// Engine: the iteration driver and the C ABI of libsqsm_b200 (include/sqsm_b200.h).  sm_100a.
+//
+// One handle = one SpconvBasedContraction object (core/core_algorithms/spconv_based_contraction.py:34-151):
+// state (contracted points, displacements, epoch, Chamfer value) lives on the device between
+// the thunks of get_pipeline(); nothing crosses PCIe per batch (the reference copies every batch
+// back with .cpu().numpy(), :107-108).
+#include "engine.h"
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+
+using namespace sqsm;
+
+struct DebugCapture {
+    bool valid = false;
+    int n_levels = 0;
+    int n_batches = 0;
+    int batch_size = 16;
+    LevelTables lv[kLevels];
+    Level0Rows rows;
+    ForwardBuffers fb;
+};
+
+struct sqsm_engine {
+    SqsmConfig cfg;
+    Ctx cx;
+    std::string err;
+    std::map<std::string, std::vector<float>> state;
+    NetWeights nw;
+    DBuf<float> P, D;
+    int64_t n = 0;
+    int epoch = 0;
+    double chamfer_prev = std::numeric_limits<double>::infinity();
+    bool early_stopped = false;
+    bool capture = false;
+    DebugCapture dbg;
+    bool prof_on = false;
+    std::map<std::string, ConvProfile> prof;
+    SkeletalResult sk;
+    bool sk_valid = false;
+    DBuf<int64_t> edges;            // cached radius graph of `sk`
+    int64_t n_edges = 0;
+    double edges_r = -1.0;
+    int64_t max_entries_per_pass = 48ll << 20;
+};
+
+static std::string g_create_error;
+
+#define SQSM_API_BEGIN(h)                                                                         \
+    if (!(h)) return 1;                                                                           \
+    try {                                                                                         \
+        SQSM_CUDA(cudaSetDevice((h)->cfg.device));
+#define SQSM_API_END(h)                                                                           \
+        return 0;                                                                                 \
+    } catch (const std::exception& e) {                                                           \
+        (h)->err = e.what();                                                                      \
+        cudaGetLastError();                                                                       \
+        return 2;                                                                                 \
+    }
+
+extern "C" int sqsm_abi_version(void) { return 1; }
+
+extern "C" const char* sqsm_last_error(sqsm_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int sqsm_create(const SqsmConfig* cfg, sqsm_handle* out) {
+    if (!cfg || !out) { g_create_error = "null argument"; return 1; }
+    *out = nullptr;
+    sqsm_engine* e = nullptr;
+    try {
+        int count = 0;
+        cudaError_t ce = cudaGetDeviceCount(&count);
+        if (ce != cudaSuccess || count == 0)
+            throw CudaError("no CUDA device: libsqsm_b200 has no CPU fallback (needs an sm_100 GPU)");
+        SQSM_CHECK(cfg->device >= 0 && cfg->device < count, "device ordinal out of range");
+        cudaDeviceProp prop;
+        SQSM_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+        if (prop.major != 10) {
+            char b[256];
+            snprintf(b, sizeof(b), "device %d (%s) is sm_%d%d; libsqsm_b200 is built for sm_100a only", cfg->device,
+                     prop.name, prop.major, prop.minor);
+            throw CudaError(b);
+        }
+        SQSM_CHECK(cfg->batch_size > 0 && cfg->voxel_size > 0.f && cfg->cube_size > 0.f && cfg->buffer_size >= 0.f,
+                   "bad configuration");
+        SQSM_CUDA(cudaSetDevice(cfg->device));
+        e = new sqsm_engine();
+        e->cfg = *cfg;
+        SQSM_CUDA(cudaStreamCreateWithFlags(&e->cx.st, cudaStreamNonBlocking));
+        cudaMemPool_t pool;
+        SQSM_CUDA(cudaDeviceGetDefaultMemPool(&pool, cfg->device));
+        uint64_t thr = UINT64_MAX;                          // keep freed blocks cached in the pool
+        SQSM_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        if (const char* env = getenv("SQSM_MAX_ENTRIES_PER_PASS")) e->max_entries_per_pass = atoll(env);
+        *out = e;
+        return 0;
+    } catch (const std::exception& ex) {
+        g_create_error = ex.what();
+        delete e;
+        return 2;
+    }
+}
+
+extern "C" void sqsm_destroy(sqsm_handle h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaStream_t st = h->cx.st;
+    cudaStreamSynchronize(st);
+    delete h;                                               // DBufs free on the stream
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+}
+
+extern "C" int sqsm_set_weight(sqsm_handle h, const char* name, const float* data, int64_t n) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(name && data && n > 0, "bad weight tensor");
+    h->state[name] = std::vector<float>(data, data + n);
+    h->nw.ready = false;
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_finalize_weights(sqsm_handle h) {
+    SQSM_API_BEGIN(h)
+    net_upload(h->cx, h->nw, h->state, h->cfg.down_kernel_flip != 0);
+    SQSM_API_END(h)
+}
+
+static void reset_state(sqsm_engine* h) {
+    h->epoch = 0;
+    h->chamfer_prev = std::numeric_limits<double>::infinity();
+    h->early_stopped = false;
+    h->sk_valid = false;
+    h->edges_r = -1.0;
+    h->dbg.valid = false;
+}
+
+__global__ void __launch_bounds__(256) k_f64_to_f32(const double* __restrict__ in, float* __restrict__ out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __double2float_rn(in[i]);           // np.copy(points).astype(np.float32) (:82)
+}
+
+extern "C" int sqsm_set_points_f64(sqsm_handle h, const double* xyz, int64_t n) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(xyz && n > 0 && n < (1ll << 31), "bad point array");
+    cudaStream_t st = h->cx.st;
+    DBuf<double> tmp(n * 3, st);
+    SQSM_CUDA(cudaMemcpyAsync(tmp.p, xyz, sizeof(double) * n * 3, cudaMemcpyHostToDevice, st));
+    h->P.alloc(n * 3, st);
+    h->D.alloc(n * 3, st);
+    h->D.zero();                                            // np.zeros_like(points) (:83)
+    k_f64_to_f32<<<div_up(n * 3, 256), 256, 0, st>>>(tmp.p, h->P.p, n * 3);
+    h->cx.launches++;
+    h->n = n;
+    reset_state(h);
+    SQSM_CUDA(cudaStreamSynchronize(st));
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_set_points_dev_f32(sqsm_handle h, const float* d_xyz, int64_t n) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(d_xyz && n > 0 && n < (1ll << 31), "bad point array");
+    cudaStream_t st = h->cx.st;
+    h->P.alloc(n * 3, st);
+    h->D.alloc(n * 3, st);
+    h->D.zero();
+    SQSM_CUDA(cudaMemcpyAsync(h->P.p, d_xyz, sizeof(float) * n * 3, cudaMemcpyDeviceToDevice, st));
+    h->n = n;
+    reset_state(h);
+    SQSM_CUDA(cudaStreamSynchronize(st));
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_set_state_f32(sqsm_handle h, const float* xyz, const float* disp, int64_t n) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(xyz && disp && n > 0 && n < (1ll << 31), "bad state arrays");
+    cudaStream_t st = h->cx.st;
+    h->P.alloc(n * 3, st);
+    h->D.alloc(n * 3, st);
+    SQSM_CUDA(cudaMemcpyAsync(h->P.p, xyz, sizeof(float) * n * 3, cudaMemcpyHostToDevice, st));
+    SQSM_CUDA(cudaMemcpyAsync(h->D.p, disp, sizeof(float) * n * 3, cudaMemcpyHostToDevice, st));
+    h->n = n;
+    reset_state(h);
+    SQSM_CUDA(cudaStreamSynchronize(st));
+    SQSM_API_END(h)
+}
+
+struct StageTimer {
+    cudaEvent_t ev[8];
+    int n = 0;
+    cudaStream_t st;
+    explicit StageTimer(cudaStream_t s) : st(s) { for (auto& e : ev) cudaEventCreate(&e); }
+    ~StageTimer() { for (auto& e : ev) cudaEventDestroy(e); }
+    void mark() { if (n < 8) cudaEventRecord(ev[n++], st); }
+    float between(int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, ev[a], ev[b]); return ms; }
+};
+
+extern "C" int sqsm_contract_step(sqsm_handle h, SqsmIterStats* stats) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(h->n > 0, "no points set");
+    SQSM_CHECK(h->nw.ready, "weights not finalised");
+    Ctx& cx = h->cx;
+    cudaStream_t st = cx.st;
+    const SqsmConfig& cfg = h->cfg;
+    SqsmIterStats s;
+    std::memset(&s, 0, sizeof(s));
+    s.chamfer = std::numeric_limits<double>::quiet_NaN();
+    h->epoch += 1;                                                          // :76
+    s.epoch = h->epoch;
+    s.n_in = h->n;
+    const int64_t launches0 = cx.launches;
+    if (h->early_stopped) {                                                 // :77-80
+        s.skipped = 1;
+        if (stats) *stats = s;
+        return 0;
+    }
+    h->sk_valid = false;
+    h->edges_r = -1.0;
+    h->dbg.valid = false;
+    float ms_tile = 0, ms_vox = 0, ms_rule = 0, ms_net = 0, ms_cd = 0;
+    StageTimer T0(st);
+    T0.mark();
+    TilingResult tl;
+    tile_points(cx, h->P.p, h->n, cfg.cube_size, cfg.buffer_size, cfg.voxel_size, cfg.batch_size, tl);   // :85-91
+    T0.mark();
+    s.n_entries = tl.n_entries;
+    s.n_cubes = tl.n_samples;
+    s.n_batches = tl.n_batches;
+    DBuf<float> newP(tl.n_entries * 3, st), newD(tl.n_entries * 3, st);
+    int64_t out_base = 0;
+    int passes = 0;
+    for (int s0 = 0; s0 < tl.n_samples;) {
+        // a pass = as many whole batches (cfg.batch_size cubes) as fit the entry budget
+        int s1 = s0;
+        while (s1 < tl.n_samples) {
+            int nxt = std::min(s1 + cfg.batch_size, tl.n_samples);
+            if (s1 > s0 && tl.start[nxt] - tl.start[s0] > h->max_entries_per_pass) break;
+            s1 = nxt;
+        }
+        ++passes;
+        const int batch0 = s0 / cfg.batch_size;
+        const int nb = (s1 - 1) / cfg.batch_size - batch0 + 1;
+        StageTimer T(st);
+        T.mark();
+        LevelTables lv[kLevels];
+        Level0Rows rows;
+        DBuf<int32_t> ent_row;
+        int64_t n_out = 0;
+        build_level0(cx, h->P.p, h->D.p, tl, s0, s1, cfg.batch_size, cfg.voxel_size, lv[0], rows, out_base, &n_out, ent_row);
+        ent_row.release();
+        T.mark();
+        int64_t far = 0;
+        build_subm(cx, lv[0], batch0, nb, cfg.batch_size, &far);
+        s.far_face_rows += far;
+        int n_levels = 1;
+        for (int l = 0; l + 1 < kLevels; ++l) {
+            if (!build_down(cx, lv[l], lv[l + 1], batch0, nb, cfg.batch_size)) break;
+            build_subm(cx, lv[l + 1], batch0, nb, cfg.batch_size, nullptr);
+            n_levels = l + 2;
+        }
+        T.mark();
+        s.n_vox += lv[0].n;
+        s.pairs_l0 += lv[0].pairs;
+        if (n_levels > 1) { s.n_rows_l1 += lv[1].n; s.pairs_l1 += lv[1].pairs; }
+        if (n_levels > 2) { s.n_rows_l2 += lv[2].n; s.pairs_l2 += lv[2].pairs; }
+        if (n_levels > 3) { s.n_rows_l3 += lv[3].n; s.pairs_l3 += lv[3].pairs; }
+        ForwardBuffers fb;
+        net_forward(cx, h->nw, lv, rows, n_levels, fb, h->capture, newP.p, newD.p, h->prof_on ? &h->prof : nullptr);  // :100-108
+        T.mark();
+        SQSM_CUDA(cudaStreamSynchronize(st));
+        ms_vox += T.between(0, 1);
+        ms_rule += T.between(1, 2);
+        ms_net += T.between(2, 3);
+        out_base += n_out;
+        if (h->capture) {
+            SQSM_CHECK(s0 == 0 && s1 == tl.n_samples,
+                       "debug capture needs the whole iteration in one pass (raise SQSM_MAX_ENTRIES_PER_PASS)");
+            DebugCapture& d = h->dbg;
+            d.n_levels = n_levels;
+            d.n_batches = nb;
+            d.batch_size = cfg.batch_size;
+            for (int l = 0; l < kLevels; ++l) d.lv[l] = std::move(lv[l]);
+            d.rows = std::move(rows);
+            d.fb = std::move(fb);
+            d.valid = true;
+        }
+        s0 = s1;
+    }
+    s.n_out = out_base;
+    SQSM_CHECK(out_base > 0, "contraction produced no interior voxel");
+    bool accept = true;
+    if (cfg.monitored_by_chamfer_distance) {                                 // :112-128
+        StageTimer T(st);
+        T.mark();
+        double cd = chamfer_distance(cx, h->P.p, h->n, newP.p, out_base, (double)cfg.voxel_size);
+        T.mark();
+        SQSM_CUDA(cudaStreamSynchronize(st));
+        ms_cd = T.between(0, 1);
+        s.chamfer = cd;
+        if (cd > h->chamfer_prev) {
+            accept = false;
+            if (cfg.latch_early_stop) h->early_stopped = true;
+        } else {
+            h->chamfer_prev = cd;
+        }
+    }
+    if (accept) {                                                            // :130-131
+        h->P = std::move(newP);
+        h->D = std::move(newD);
+        h->n = out_base;
+    }
+    SQSM_CUDA(cudaStreamSynchronize(st));
+    ms_tile = T0.between(0, 1);
+    s.accepted = accept ? 1 : 0;
+    s.gpu_launches = (int32_t)(cx.launches - launches0);
+    s.ms_tiling = ms_tile; s.ms_voxel = ms_vox; s.ms_rulebook = ms_rule; s.ms_network = ms_net; s.ms_chamfer = ms_cd;
+    (void)passes;
+    if (stats) *stats = s;
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_result_size(sqsm_handle h, int64_t* n) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(n, "null argument");
+    *n = h->n;
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_get_result(sqsm_handle h, float* pts, float* disp) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(h->n > 0, "no state");
+    cudaStream_t st = h->cx.st;
+    if (pts) SQSM_CUDA(cudaMemcpyAsync(pts, h->P.p, sizeof(float) * h->n * 3, cudaMemcpyDeviceToHost, st));
+    if (disp) SQSM_CUDA(cudaMemcpyAsync(disp, h->D.p, sizeof(float) * h->n * 3, cudaMemcpyDeviceToHost, st));
+    SQSM_CUDA(cudaStreamSynchronize(st));
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_skeletal_sample(sqsm_handle h, double voxel, int64_t* m, int64_t* ids, float* pts, float* radii) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(h->n > 0 && m, "no state");
+    cudaStream_t st = h->cx.st;
+    if (!h->sk_valid) {
+        skeletal_sample(h->cx, h->P.p, h->D.p, h->n, voxel, h->sk);
+        h->sk_valid = true;
+        h->edges_r = -1.0;
+    }
+    *m = h->sk.m;
+    if (ids) SQSM_CUDA(cudaMemcpyAsync(ids, h->sk.ids.p, sizeof(int64_t) * h->sk.m, cudaMemcpyDeviceToHost, st));
+    if (pts) SQSM_CUDA(cudaMemcpyAsync(pts, h->sk.pts.p, sizeof(float) * h->sk.m * 3, cudaMemcpyDeviceToHost, st));
+    if (radii) SQSM_CUDA(cudaMemcpyAsync(radii, h->sk.radii.p, sizeof(float) * h->sk.m, cudaMemcpyDeviceToHost, st));
+    SQSM_CUDA(cudaStreamSynchronize(st));
+    SQSM_API_END(h)
+}
+
+static void edges_out(sqsm_engine* h, const float* d_pts, int64_t m, double r, int64_t* n_edges, int64_t* out,
+                      int64_t capacity) {
+    DBuf<int64_t> edges;
+    int64_t E = 0;
+    radius_graph(h->cx, d_pts, m, r, edges, &E);
+    *n_edges = E;
+    if (out && E > 0) {
+        SQSM_CHECK(capacity < 0 || E <= capacity, "edge buffer too small");
+        SQSM_CUDA(cudaMemcpyAsync(out, edges.p, sizeof(int64_t) * 2 * E, cudaMemcpyDeviceToHost, h->cx.st));
+    }
+    SQSM_CUDA(cudaStreamSynchronize(h->cx.st));
+}
+
+extern "C" int sqsm_radius_graph(sqsm_handle h, double r, int64_t* n_edges, int64_t* out) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(h->sk_valid && n_edges, "call sqsm_skeletal_sample first");
+    if (h->edges_r != r) {                                   // computed once per skeletal sample and radius
+        radius_graph(h->cx, h->sk.pts.p, h->sk.m, r, h->edges, &h->n_edges);
+        h->edges_r = r;
+    }
+    *n_edges = h->n_edges;
+    if (out && h->n_edges > 0)
+        SQSM_CUDA(cudaMemcpyAsync(out, h->edges.p, sizeof(int64_t) * 2 * h->n_edges, cudaMemcpyDeviceToHost, h->cx.st));
+    SQSM_CUDA(cudaStreamSynchronize(h->cx.st));
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_radius_graph_points(sqsm_handle h, const float* pts, int64_t m, double r, int64_t* n_edges,
+                                        int64_t* out, int64_t capacity) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(pts && m > 0 && n_edges, "bad arguments");
+    DBuf<float> d(m * 3, h->cx.st);
+    SQSM_CUDA(cudaMemcpyAsync(d.p, pts, sizeof(float) * m * 3, cudaMemcpyHostToDevice, h->cx.st));
+    edges_out(h, d.p, m, r, n_edges, out, capacity);
+    SQSM_API_END(h)
+}
+
+// ---------------------------------------------------------------------------------- inspection hooks
+
+extern "C" int sqsm_debug_capture(sqsm_handle h, int32_t enable) {
+    SQSM_API_BEGIN(h)
+    h->capture = enable != 0;
+    if (!enable) h->dbg = DebugCapture();
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_debug_level_size(sqsm_handle h, int32_t level, int64_t* n) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(h->dbg.valid && n && level >= 0 && level < kLevels, "no capture");
+    *n = level < h->dbg.n_levels ? h->dbg.lv[level].n : 0;
+    SQSM_API_END(h)
+}
+
+static void row_coords_host(sqsm_engine* h, const LevelTables& L, std::vector<int32_t>& coords) {
+    auto bricks = L.map.bricks.to_host();
+    auto rb = L.row_brick.to_host();
+    auto rp = L.row_pos.to_host();
+    (void)h;
+    coords.resize((size_t)L.n * 4);
+    for (int64_t r = 0; r < L.n; ++r) {
+        uint64_t key = bricks[rb[r]].key;
+        uint32_t pos = rp[r];
+        coords[4 * r + 0] = (int32_t)key_s(key);
+        coords[4 * r + 1] = (int32_t)key_z(key) * 8 + (int32_t)(pos >> 6);
+        coords[4 * r + 2] = (int32_t)key_y(key) * 8 + (int32_t)((pos >> 3) & 7);
+        coords[4 * r + 3] = (int32_t)key_x(key) * 8 + (int32_t)(pos & 7);
+    }
+}
+
+extern "C" int sqsm_debug_voxels(sqsm_handle h, int32_t* indices, int64_t* winner, uint8_t* mask) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(h->dbg.valid, "no capture");
+    const DebugCapture& d = h->dbg;
+    std::vector<int32_t> coords;
+    row_coords_host(h, d.lv[0], coords);
+    auto canon = d.rows.canon.to_host();
+    auto pt = d.rows.pt.to_host();
+    auto in = d.rows.interior.to_host();
+    for (int64_t r = 0; r < d.lv[0].n; ++r) {
+        int64_t c = canon[r];
+        if (indices) for (int k = 0; k < 4; ++k) indices[4 * c + k] = coords[4 * r + k];
+        if (winner) winner[c] = pt[r];
+        if (mask) mask[c] = in[r];
+    }
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_debug_batch_shapes(sqsm_handle h, int32_t* shapes, int32_t* descend) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(h->dbg.valid, "no capture");
+    const DebugCapture& d = h->dbg;
+    if (shapes) {
+        auto s = d.lv[0].shape.to_host();
+        std::memcpy(shapes, s.data(), s.size() * sizeof(int32_t));
+    }
+    if (descend) {
+        for (int l = 0; l < kLevels - 1; ++l) {
+            for (int b = 0; b < d.n_batches; ++b) descend[l * d.n_batches + b] = 0;
+            if (l < d.n_levels && d.lv[l].desc.n == d.n_batches) {
+                auto f = d.lv[l].desc.to_host();
+                for (int b = 0; b < d.n_batches; ++b) descend[l * d.n_batches + b] = f[b];
+            }
+        }
+    }
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_debug_level_tables(sqsm_handle h, int32_t level, int32_t* coords, int32_t* nbr, int32_t* parent,
+                                       int32_t* koff) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(h->dbg.valid && level >= 0 && level < h->dbg.n_levels, "no capture for this level");
+    const LevelTables& L = h->dbg.lv[level];
+    if (coords) {
+        std::vector<int32_t> c;
+        row_coords_host(h, L, c);
+        std::memcpy(coords, c.data(), c.size() * sizeof(int32_t));
+    }
+    if (nbr) { auto v = L.nbr.to_host(); std::memcpy(nbr, v.data(), v.size() * sizeof(int32_t)); }
+    if (parent) {
+        SQSM_CHECK(L.parent.n == L.n, "level has no down-sample tables");
+        auto v = L.parent.to_host();
+        std::memcpy(parent, v.data(), v.size() * sizeof(int32_t));
+    }
+    if (koff) {
+        SQSM_CHECK(L.koff.n == L.n, "level has no down-sample tables");
+        auto v = L.koff.to_host();
+        std::memcpy(koff, v.data(), v.size() * sizeof(int32_t));
+    }
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_debug_canon_to_internal(sqsm_handle h, int32_t* perm) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(h->dbg.valid && perm, "no capture");
+    auto canon = h->dbg.rows.canon.to_host();
+    for (int64_t r = 0; r < (int64_t)canon.size(); ++r) perm[canon[r]] = (int32_t)r;
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_debug_predictions(sqsm_handle h, float* pred, float* offset, float* regression) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(h->dbg.valid && h->dbg.fb.pred.n > 0, "no capture");
+    auto p = h->dbg.fb.pred.to_host();
+    auto o = h->dbg.fb.offset.to_host();
+    int64_t n0 = h->dbg.lv[0].n;
+    for (int64_t r = 0; r < n0; ++r) {
+        if (pred) for (int k = 0; k < 3; ++k) pred[3 * r + k] = p[4 * r + k];
+        if (offset) for (int k = 0; k < 3; ++k) offset[3 * r + k] = o[4 * r + k];
+        if (regression) regression[r] = o[4 * r + 3];
+    }
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_debug_features(sqsm_handle h, const char* stage, int32_t* level, int32_t* channels, float* data,
+                                   int64_t capacity) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(h->dbg.valid && stage, "no capture");
+    auto it = h->dbg.fb.keep.find(stage);
+    SQSM_CHECK(it != h->dbg.fb.keep.end(), "unknown stage");
+    auto meta = h->dbg.fb.keep_meta.at(stage);
+    if (level) *level = meta.first;
+    if (channels) *channels = meta.second;
+    if (data) {
+        SQSM_CHECK(capacity >= it->second.n, "feature buffer too small");
+        auto v = it->second.to_host();
+        std::memcpy(data, v.data(), v.size() * sizeof(float));
+    }
+    SQSM_API_END(h)
+}
+
+// ---------------------------------------------------------------------------------- measurement hooks
+
+extern "C" int sqsm_profile_enable(sqsm_handle h, int32_t enable) {
+    SQSM_API_BEGIN(h)
+    h->prof_on = enable != 0;
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_profile_reset(sqsm_handle h) {
+    SQSM_API_BEGIN(h)
+    h->prof.clear();
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_profile_get(sqsm_handle h, const char* family, double* ms, int64_t* launches, double* bytes) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(family, "null family");
+    ConvProfile p;
+    auto it = h->prof.find(family);
+    if (it != h->prof.end()) p = it->second;
+    if (ms) *ms = p.ms;
+    if (launches) *launches = p.launches;
+    if (bytes) *bytes = p.bytes;
+    SQSM_API_END(h)
+}

@@ -1,0 +1,502 @@
+// Chamfer monitor, skeletal sampling + radii, radius-neighbour edge set.  sm_100a.
+//
+// Replaces, on the device:
+//   Chamfer monitor      core/core_algorithms/spconv_based_contraction.py:112-128
+//                        (Open3D voxel_down_sample_and_trace x2 + compute_point_cloud_distance x2)
+//   skeletal sampling    core/thinning_based_skeletonization_pipeline.py:68-80
+//   radius edges         core/skeletonization_pipeline_base.py:132-144 merged/sorted at :158
+//                        (SciPy cKDTree.query_ball_point + Python double loop + np.unique)
+// All three run on the BrickMap: an 8-voxel brick is the search cell; exact nearest neighbours
+// are found by growing rings of bricks until the best distance is below the ring's lower bound.
+#include "engine.h"
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+namespace sqsm {
+
+// ---------------------------------------------------------------------------------- bounds
+
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+static float ord2f(uint32_t o) {
+    uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+// per-axis min / max of an [n][3] float cloud -> 6 order-preserving uint32 (min x,y,z, max x,y,z)
+__global__ void __launch_bounds__(256) k_bounds(const float* __restrict__ P, int64_t n, uint32_t* __restrict__ out) {
+    uint32_t mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        #pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            uint32_t o = f2ord(P[3 * i + a]);
+            mn[a] = min(mn[a], o);
+            mx[a] = max(mx[a], o);
+        }
+    }
+    #pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        mn[a] = __reduce_min_sync(0xFFFFFFFFu, mn[a]);
+        mx[a] = __reduce_max_sync(0xFFFFFFFFu, mx[a]);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        #pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(&out[a], mn[a]);
+            atomicMax(&out[3 + a], mx[a]);
+        }
+    }
+}
+
+static void cloud_bounds(Ctx& cx, const float* d_P, int64_t n, double mn[3], double mx[3]) {
+    DBuf<uint32_t> b(6, cx.st);
+    uint32_t init[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};
+    SQSM_CUDA(cudaMemcpyAsync(b.p, init, sizeof(init), cudaMemcpyHostToDevice, cx.st));
+    int grid = std::min<int64_t>(div_up(n, 256), kNumSMs * 8);
+    k_bounds<<<grid, 256, 0, cx.st>>>(d_P, n, b.p);
+    cx.launches++;
+    uint32_t h[6];
+    SQSM_CUDA(cudaMemcpyAsync(h, b.p, sizeof(h), cudaMemcpyDeviceToHost, cx.st));
+    SQSM_CUDA(cudaStreamSynchronize(cx.st));
+    for (int a = 0; a < 3; ++a) { mn[a] = (double)ord2f(h[a]); mx[a] = (double)ord2f(h[3 + a]); }
+}
+
+// ---------------------------------------------------------------------------------- global voxel grid
+
+struct GridParams { double mn[3]; double voxel; };
+
+// Open3D voxel_down_sample_and_trace: voxel index = floor((p - min_bound) / voxel) in float64
+__device__ __forceinline__ bool grid_voxel(const float* __restrict__ P, int64_t i, const GridParams& g, int v[3]) {
+    bool ok = true;
+    #pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double f = floor(__ddiv_rn(__dsub_rn((double)P[3 * i + a], g.mn[a]), g.voxel));
+        ok = ok && (f >= 0.0) && (f < 524288.0);          // 65536 bricks x 8 voxels per axis
+        v[a] = (int)f;
+    }
+    return ok;
+}
+
+__global__ void __launch_bounds__(256) k_grid_entries(const float* __restrict__ P, int64_t n, const __grid_constant__ GridParams g,
+                                                      uint64_t* __restrict__ ent_key, uint16_t* __restrict__ ent_pos,
+                                                      int32_t* __restrict__ err) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int v[3];
+    if (!grid_voxel(P, i, g, v)) { ent_key[i] = kEmptyKey; ent_pos[i] = 0; atomicOr(err, 1); return; }
+    ent_key[i] = pack_key(0u, (uint32_t)(v[2] >> 3), (uint32_t)(v[1] >> 3), (uint32_t)(v[0] >> 3));
+    ent_pos[i] = (uint16_t)pos_of(v[2] & 7, v[1] & 7, v[0] & 7);
+}
+
+struct GridMap {
+    BrickMap map;
+    DBuf<int32_t> pt_row;      // [n] voxel row of every point
+    GridParams g;
+};
+
+__global__ void __launch_bounds__(256) k_point_rows(const Brick* __restrict__ bricks, const int32_t* __restrict__ ent_brick,
+                                                    const uint16_t* __restrict__ ent_pos, int64_t n, int32_t* __restrict__ pt_row) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int b = ent_brick[i];
+    pt_row[i] = (b < 0) ? -1 : brick_row(&bricks[b], ent_pos[i]);
+}
+
+static void grid_build(Ctx& cx, const float* d_P, int64_t n, const double mn[3], double voxel, GridMap& gm) {
+    cudaStream_t st = cx.st;
+    for (int a = 0; a < 3; ++a) gm.g.mn[a] = mn[a];
+    gm.g.voxel = voxel;
+    DBuf<uint64_t> ent_key(n, st);
+    DBuf<uint16_t> ent_pos(n, st);
+    DBuf<int32_t> ent_brick(n, st);
+    DBuf<int32_t> err(1, st);
+    err.zero();
+    k_grid_entries<<<div_up(n, 256), 256, 0, st>>>(d_P, n, gm.g, ent_key.p, ent_pos.p, err.p);
+    cx.launches++;
+    brickmap_build(cx, gm.map, ent_key.p, ent_pos.p, n, ent_brick.p);
+    int32_t herr = 0;
+    SQSM_CUDA(cudaMemcpyAsync(&herr, err.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    gm.pt_row.alloc(n, st);
+    k_point_rows<<<div_up(n, 256), 256, 0, st>>>(gm.map.bricks.p, ent_brick.p, ent_pos.p, n, gm.pt_row.p);
+    cx.launches++;
+    SQSM_CUDA(cudaStreamSynchronize(st));
+    SQSM_CHECK(herr == 0, "cloud extent exceeds 524288 voxels per axis (or NaN coordinates)");
+}
+
+// ---------------------------------------------------------------------------------- Chamfer monitor
+
+__global__ void __launch_bounds__(256) k_voxel_accumulate(const float* __restrict__ P, const int32_t* __restrict__ pt_row,
+                                                          int64_t n, double* __restrict__ sum, int32_t* __restrict__ cnt) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int r = pt_row[i];
+    if (r < 0) return;
+    atomicAdd(&sum[3 * (size_t)r + 0], (double)P[3 * i + 0]);
+    atomicAdd(&sum[3 * (size_t)r + 1], (double)P[3 * i + 1]);
+    atomicAdd(&sum[3 * (size_t)r + 2], (double)P[3 * i + 2]);
+    atomicAdd(&cnt[r], 1);
+}
+
+__global__ void __launch_bounds__(256) k_voxel_mean(double* __restrict__ sum, const int32_t* __restrict__ cnt, int64_t rows) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    double c = (double)cnt[r];
+    sum[3 * r + 0] = __ddiv_rn(sum[3 * r + 0], c);
+    sum[3 * r + 1] = __ddiv_rn(sum[3 * r + 1], c);
+    sum[3 * r + 2] = __ddiv_rn(sum[3 * r + 2], c);
+}
+
+// One block per query brick of map A; candidates are the voxel means of map B in the 27 bricks around
+// it, staged brick by brick through shared memory.  A query whose best distance exceeds the lower
+// bound of the searched 3x3x3 block continues with growing rings of bricks (exact 1-NN).
+constexpr int kNNThreads = 128;
+__global__ void __launch_bounds__(kNNThreads) k_nn_sqdist(const Brick* __restrict__ A, int nA, const double* __restrict__ meanA,
+                                                          BrickHash hB, const Brick* __restrict__ B, const double* __restrict__ meanB,
+                                                          double brick_edge, int max_ring, double* __restrict__ acc) {
+    __shared__ double cand[512 * 3];
+    __shared__ int s_nb[27];
+    __shared__ double s_red[kNNThreads / 32];
+    const int t = threadIdx.x;
+    double local_sum = 0.0;
+    for (int a = blockIdx.x; a < nA; a += gridDim.x) {
+        const Brick& qa = A[a];
+        const uint64_t key = qa.key;
+        const int bz = (int)key_z(key), by = (int)key_y(key), bx = (int)key_x(key);
+        __syncthreads();
+        if (t < 27) {
+            int z = bz + t / 9 - 1, y = by + (t / 3) % 3 - 1, x = bx + t % 3 - 1;
+            int id = -1;
+            if (z >= 0 && y >= 0 && x >= 0 && z < 65536 && y < 65536 && x < 65536)
+                id = hash_find(hB, pack_key(0u, (uint32_t)z, (uint32_t)y, (uint32_t)x));
+            s_nb[t] = id;
+        }
+        __syncthreads();
+        const int nq = qa.count;
+        constexpr int QPT = 512 / kNNThreads;
+        double q[QPT][3], best[QPT];
+        #pragma unroll
+        for (int j = 0; j < QPT; ++j) {
+            int qi = t + j * kNNThreads;
+            best[j] = 1e300;
+            if (qi < nq) {
+                q[j][0] = meanA[3 * (size_t)(qa.base + qi) + 0];
+                q[j][1] = meanA[3 * (size_t)(qa.base + qi) + 1];
+                q[j][2] = meanA[3 * (size_t)(qa.base + qi) + 2];
+            } else { q[j][0] = q[j][1] = q[j][2] = 0.0; }
+        }
+        for (int nb = 0; nb < 27; ++nb) {
+            int id = s_nb[nb];
+            if (id < 0) continue;                                   // block-uniform
+            const int cbase = B[id].base, cn = B[id].count;
+            __syncthreads();
+            for (int i = t; i < cn * 3; i += kNNThreads) cand[i] = meanB[3 * (size_t)cbase + i];
+            __syncthreads();
+            #pragma unroll
+            for (int j = 0; j < QPT; ++j) {
+                if (t + j * kNNThreads >= nq) continue;
+                double bj = best[j];
+                for (int c = 0; c < cn; ++c) {
+                    double dx = q[j][0] - cand[3 * c], dy = q[j][1] - cand[3 * c + 1], dz = q[j][2] - cand[3 * c + 2];
+                    double d2 = dx * dx + dy * dy + dz * dz;
+                    bj = fmin(bj, d2);
+                }
+                best[j] = bj;
+            }
+        }
+        // exactness: the query lies inside brick b; once every brick within Chebyshev distance R of b has
+        // been searched, any other point is at least R * brick_edge away.  R = 1 after the 27-neighbourhood.
+        #pragma unroll
+        for (int j = 0; j < QPT; ++j) {
+            if (t + j * kNNThreads >= nq) continue;
+            int ring = 1;
+            double bj = best[j];
+            while (bj > (double)ring * brick_edge * (double)ring * brick_edge && ring < max_ring) {
+                ++ring;
+                for (int dz = -ring; dz <= ring; ++dz)
+                    for (int dy = -ring; dy <= ring; ++dy)
+                        for (int dx = -ring; dx <= ring; ++dx) {
+                            if (max(max(abs(dz), abs(dy)), abs(dx)) != ring) continue;
+                            int z = bz + dz, y = by + dy, x = bx + dx;
+                            if (z < 0 || y < 0 || x < 0 || z > 65535 || y > 65535 || x > 65535) continue;
+                            int id = hash_find(hB, pack_key(0u, (uint32_t)z, (uint32_t)y, (uint32_t)x));
+                            if (id < 0) continue;
+                            const int cbase = B[id].base, cn = B[id].count;
+                            for (int c = 0; c < cn; ++c) {
+                                double ddx = q[j][0] - meanB[3 * (size_t)(cbase + c)], ddy = q[j][1] - meanB[3 * (size_t)(cbase + c) + 1],
+                                       ddz = q[j][2] - meanB[3 * (size_t)(cbase + c) + 2];
+                                bj = fmin(bj, ddx * ddx + ddy * ddy + ddz * ddz);
+                            }
+                        }
+            }
+            local_sum += bj;
+        }
+    }
+    // block reduction of the squared distances
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) local_sum += __shfl_xor_sync(0xFFFFFFFFu, local_sum, d);
+    __syncthreads();
+    if ((t & 31) == 0) s_red[t >> 5] = local_sum;
+    __syncthreads();
+    if (t == 0) {
+        double s = 0.0;
+        for (int w = 0; w < kNNThreads / 32; ++w) s += s_red[w];
+        atomicAdd(acc, s);
+    }
+}
+
+struct VoxelMeans {
+    GridMap gm;
+    DBuf<double> mean;         // [rows][3]
+};
+
+static void voxel_means(Ctx& cx, const float* d_P, int64_t n, const double mn[3], double voxel, VoxelMeans& vm) {
+    cudaStream_t st = cx.st;
+    grid_build(cx, d_P, n, mn, voxel, vm.gm);
+    int64_t rows = vm.gm.map.n_rows;
+    vm.mean.alloc(rows * 3, st);
+    vm.mean.zero();
+    DBuf<int32_t> cnt(rows, st);
+    cnt.zero();
+    k_voxel_accumulate<<<div_up(n, 256), 256, 0, st>>>(d_P, vm.gm.pt_row.p, n, vm.mean.p, cnt.p);
+    k_voxel_mean<<<div_up(rows, 256), 256, 0, st>>>(vm.mean.p, cnt.p, rows);
+    cx.launches += 2;
+}
+
+double chamfer_distance(Ctx& cx, const float* d_P, int64_t np, const float* d_Q, int64_t nq, double voxel) {
+    cudaStream_t st = cx.st;
+    SQSM_CHECK(np > 0 && nq > 0, "Chamfer monitor needs two non-empty clouds");
+    double mnP[3], mxP[3], mnQ[3], mxQ[3], mn[3], mx[3];
+    cloud_bounds(cx, d_P, np, mnP, mxP);
+    cloud_bounds(cx, d_Q, nq, mnQ, mxQ);
+    for (int a = 0; a < 3; ++a) { mn[a] = std::min(mnP[a], mnQ[a]); mx[a] = std::max(mxP[a], mxQ[a]); }   // :116-117
+    VoxelMeans A, B;
+    voxel_means(cx, d_P, np, mn, voxel, A);                                                                // :120
+    voxel_means(cx, d_Q, nq, mn, voxel, B);                                                                // :121
+    double ext = 0;
+    for (int a = 0; a < 3; ++a) ext = std::max(ext, mx[a] - mn[a]);
+    const double edge = 8.0 * voxel;
+    int max_ring = (int)std::ceil(ext / edge) + 2;
+    DBuf<double> acc(2, st);
+    acc.zero();
+    int gA = std::min(A.gm.map.n_bricks, kNumSMs * 16), gB = std::min(B.gm.map.n_bricks, kNumSMs * 16);
+    k_nn_sqdist<<<gA, kNNThreads, 0, st>>>(A.gm.map.bricks.p, A.gm.map.n_bricks, A.mean.p, B.gm.map.view(),
+                                           B.gm.map.bricks.p, B.mean.p, edge, max_ring, acc.p);
+    k_nn_sqdist<<<gB, kNNThreads, 0, st>>>(B.gm.map.bricks.p, B.gm.map.n_bricks, B.mean.p, A.gm.map.view(),
+                                           A.gm.map.bricks.p, A.mean.p, edge, max_ring, acc.p + 1);
+    cx.launches += 2;
+    double h[2];
+    SQSM_CUDA(cudaMemcpyAsync(h, acc.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    SQSM_CUDA(cudaStreamSynchronize(st));
+    return h[0] / (double)A.gm.map.n_rows + h[1] / (double)B.gm.map.n_rows;                                // :122
+}
+
+// ---------------------------------------------------------------------------------- skeletal sampling
+
+__global__ void __launch_bounds__(256) k_min_index(const int32_t* __restrict__ pt_row, int64_t n, uint32_t* __restrict__ winner) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int r = pt_row[i];
+    if (r >= 0) atomicMin(&winner[r], (uint32_t)i);
+}
+
+__global__ void __launch_bounds__(256) k_is_first(const int32_t* __restrict__ pt_row, const uint32_t* __restrict__ winner,
+                                                  int64_t n, int32_t* __restrict__ flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    int f = 0;
+    if (i < n) { int r = pt_row[i]; f = (r >= 0 && winner[r] == (uint32_t)i) ? 1 : 0; }
+    flag[i] = f;
+}
+
+// skeletal_points = contracted[ids]; radii = ||displacement[ids]||_2 computed like np.linalg.norm on float32:
+// sqrt(add.reduce(x*x)) with float32 multiplies and adds in index order, no FMA.
+__global__ void __launch_bounds__(256) k_skeletal_gather(const float* __restrict__ P, const float* __restrict__ D,
+                                                         const int32_t* __restrict__ flag, const int32_t* __restrict__ scan,
+                                                         int64_t n, int64_t* __restrict__ ids, float* __restrict__ pts,
+                                                         float* __restrict__ radii) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flag[i]) return;
+    int o = scan[i];
+    ids[o] = i;
+    pts[3 * (size_t)o + 0] = P[3 * i + 0]; pts[3 * (size_t)o + 1] = P[3 * i + 1]; pts[3 * (size_t)o + 2] = P[3 * i + 2];
+    float dx = D[3 * i + 0], dy = D[3 * i + 1], dz = D[3 * i + 2];
+    float s = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    radii[o] = __fsqrt_rn(s);
+}
+
+void skeletal_sample(Ctx& cx, const float* d_P, const float* d_D, int64_t n, double voxel, SkeletalResult& out) {
+    cudaStream_t st = cx.st;
+    SQSM_CHECK(n > 0, "no contracted points");
+    double mn[3], mx[3];
+    cloud_bounds(cx, d_P, n, mn, mx);                                 // cloud.get_min_bound() (thinning...py:76)
+    GridMap gm;
+    grid_build(cx, d_P, n, mn, voxel, gm);
+    int64_t rows = gm.map.n_rows;
+    DBuf<uint32_t> winner(rows, st);
+    winner.fill_ff();
+    k_min_index<<<div_up(n, 256), 256, 0, st>>>(gm.pt_row.p, n, winner.p);
+    DBuf<int32_t> flag(n + 1, st), scan(n + 1, st);
+    k_is_first<<<div_up(n + 1, 256), 256, 0, st>>>(gm.pt_row.p, winner.p, n, flag.p);
+    cx.launches += 2;
+    exclusive_scan_i32(cx, flag.p, scan.p, n + 1);
+    out.m = rows;
+    out.ids.alloc(rows, st);
+    out.pts.alloc(rows * 3, st);
+    out.radii.alloc(rows, st);
+    k_skeletal_gather<<<div_up(n, 256), 256, 0, st>>>(d_P, d_D, flag.p, scan.p, n, out.ids.p, out.pts.p, out.radii.p);
+    cx.launches++;
+    int32_t tot = 0;
+    SQSM_CUDA(cudaMemcpyAsync(&tot, scan.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SQSM_CUDA(cudaStreamSynchronize(st));
+    SQSM_CHECK(tot == rows, "internal error: skeletal sample count != voxel count");
+}
+
+// ---------------------------------------------------------------------------------- radius graph
+
+__global__ void __launch_bounds__(256) k_cell_entries(const float* __restrict__ P, int64_t n, const __grid_constant__ GridParams g,
+                                                      uint64_t* __restrict__ ent_key, uint16_t* __restrict__ ent_pos,
+                                                      int32_t* __restrict__ err) {
+    // cells of edge g.voxel: one brick per cell (pos unused)
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int v[3];
+    bool ok = true;
+    #pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double f = floor(((double)P[3 * i + a] - g.mn[a]) / g.voxel);
+        ok = ok && (f >= 0.0) && (f < 65536.0);
+        v[a] = (int)f;
+    }
+    if (!ok) { ent_key[i] = kEmptyKey; ent_pos[i] = 0; atomicOr(err, 1); return; }
+    ent_key[i] = pack_key(0u, (uint32_t)v[2], (uint32_t)v[1], (uint32_t)v[0]);
+    ent_pos[i] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_cell_count(const int32_t* __restrict__ ent_brick, int64_t n, int32_t* __restrict__ cnt) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && ent_brick[i] >= 0) atomicAdd(&cnt[ent_brick[i]], 1);
+}
+
+// mode 0: count neighbours j > i within r; mode 1: write them at off[i]
+template <int MODE>
+__global__ void __launch_bounds__(256) k_radius_pairs(const float* __restrict__ P, const uint32_t* __restrict__ order,
+                                                      const uint32_t* __restrict__ cell_of, int64_t n,
+                                                      const int32_t* __restrict__ bnbr, const int32_t* __restrict__ cstart,
+                                                      double r2, int32_t* __restrict__ cnt, const int64_t* __restrict__ off,
+                                                      int64_t* __restrict__ edges) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t i = order[s];
+    const int cell = (int)cell_of[s];
+    const double x = (double)P[3 * (size_t)i], y = (double)P[3 * (size_t)i + 1], z = (double)P[3 * (size_t)i + 2];
+    int c = 0;
+    int64_t o = (MODE == 1) ? off[i] : 0;
+    for (int nb = 0; nb < 27; ++nb) {
+        int id = bnbr[(size_t)cell * 32 + nb];
+        if (id < 0) continue;
+        int b = cstart[id], e = cstart[id + 1];
+        for (int t = b; t < e; ++t) {
+            uint32_t j = order[t];
+            if (j <= i) continue;
+            double dx = x - (double)P[3 * (size_t)j], dy = y - (double)P[3 * (size_t)j + 1], dz = z - (double)P[3 * (size_t)j + 2];
+            double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if (d2 <= r2) {
+                if (MODE == 1) { edges[2 * (o + c)] = (int64_t)i; edges[2 * (o + c) + 1] = (int64_t)j; }
+                ++c;
+            }
+        }
+    }
+    if (MODE == 0) cnt[i] = c;
+}
+
+// ascending j inside every node's segment (the merged edge list is lexicographic, :158)
+__global__ void __launch_bounds__(256) k_sort_segments(int64_t* __restrict__ edges, const int64_t* __restrict__ off, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t b = off[i], e = off[i + 1];
+    for (int64_t a = b + 1; a < e; ++a) {
+        int64_t v = edges[2 * a + 1];
+        int64_t p = a - 1;
+        while (p >= b && edges[2 * p + 1] > v) { edges[2 * (p + 1) + 1] = edges[2 * p + 1]; --p; }
+        edges[2 * (p + 1) + 1] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_iota_u32(uint32_t* __restrict__ a, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256) k_i32_to_i64(const int32_t* __restrict__ a, int64_t* __restrict__ b, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] = (int64_t)a[i];
+}
+
+void radius_graph(Ctx& cx, const float* d_pts, int64_t m, double r, DBuf<int64_t>& edges, int64_t* n_edges) {
+    cudaStream_t st = cx.st;
+    *n_edges = 0;
+    if (m <= 1) return;
+    SQSM_CHECK(r > 0 && m < (1ll << 31), "radius graph: bad arguments");
+    double mn[3], mx[3];
+    cloud_bounds(cx, d_pts, m, mn, mx);
+    GridParams g;
+    for (int a = 0; a < 3; ++a) g.mn[a] = mn[a];
+    g.voxel = r * 1.0009765625;                         // cell edge slightly above r: 27 cells cover the ball
+    // points whose cell coordinate would overflow 16 bits: widen the cells
+    double ext = 0;
+    for (int a = 0; a < 3; ++a) ext = std::max(ext, mx[a] - mn[a]);
+    if (ext / g.voxel > 65000.0) g.voxel = ext / 65000.0;
+    DBuf<uint64_t> ent_key(m, st);
+    DBuf<uint16_t> ent_pos(m, st);
+    DBuf<int32_t> ent_brick(m, st);
+    DBuf<int32_t> err(1, st);
+    err.zero();
+    k_cell_entries<<<div_up(m, 256), 256, 0, st>>>(d_pts, m, g, ent_key.p, ent_pos.p, err.p);
+    cx.launches++;
+    BrickMap map;
+    brickmap_build(cx, map, ent_key.p, ent_pos.p, m, ent_brick.p);
+    int32_t herr = 0;
+    SQSM_CUDA(cudaMemcpyAsync(&herr, err.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SQSM_CUDA(cudaStreamSynchronize(st));
+    SQSM_CHECK(herr == 0, "radius graph: non-finite coordinates");
+    brickmap_build_neighbours(cx, map);
+    const int nc = map.n_bricks;
+    // cell lists: points sorted by cell id (stable -> ascending point index inside a cell)
+    DBuf<int32_t> ccnt((int64_t)nc + 1, st), cstart((int64_t)nc + 1, st);
+    ccnt.zero();
+    k_cell_count<<<div_up(m, 256), 256, 0, st>>>(ent_brick.p, m, ccnt.p);
+    exclusive_scan_i32(cx, ccnt.p, cstart.p, (int64_t)nc + 1);
+    DBuf<uint32_t> iota(m, st), order(m, st), cell_sorted(m, st);
+    k_iota_u32<<<div_up(m, 256), 256, 0, st>>>(iota.p, m);
+    cx.launches += 2;
+    int bits = 1;
+    while ((1ll << bits) < nc) ++bits;
+    sort_pairs_u32(cx, (const uint32_t*)ent_brick.p, cell_sorted.p, iota.p, order.p, m, 0, bits);
+    // count, scan, fill
+    DBuf<int32_t> cnt(m + 1, st);
+    SQSM_CUDA(cudaMemsetAsync(cnt.p + m, 0, sizeof(int32_t), st));
+    const double r2 = r * r;
+    k_radius_pairs<0><<<div_up(m, 256), 256, 0, st>>>(d_pts, order.p, cell_sorted.p, m, map.bnbr.p, cstart.p, r2, cnt.p,
+                                                      nullptr, nullptr);
+    DBuf<int64_t> cnt64(m + 1, st), off(m + 1, st);
+    k_i32_to_i64<<<div_up(m + 1, 256), 256, 0, st>>>(cnt.p, cnt64.p, m + 1);
+    cx.launches += 2;
+    exclusive_scan_i64(cx, cnt64.p, off.p, m + 1);
+    int64_t E = 0;
+    SQSM_CUDA(cudaMemcpyAsync(&E, off.p + m, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    SQSM_CUDA(cudaStreamSynchronize(st));
+    *n_edges = E;
+    if (E == 0) return;
+    edges.alloc(2 * E, st);
+    k_radius_pairs<1><<<div_up(m, 256), 256, 0, st>>>(d_pts, order.p, cell_sorted.p, m, map.bnbr.p, cstart.p, r2, nullptr,
+                                                      off.p, edges.p);
+    k_sort_segments<<<div_up(m, 256), 256, 0, st>>>(edges.p, off.p, m);
+    cx.launches += 2;
+}
+
+}  // namespace sqsm

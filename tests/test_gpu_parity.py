@@ -1,0 +1,273 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  ``-m gpu``.
+
+Integer outputs (voxel coordinates, winners, masks, batch shapes, rulebooks, skeletal sample ids,
+radius-neighbour edges) must be bit-exact; float outputs must be within the tolerance written next
+to each assertion (fp32 FFMA mode of SURVEY.md App. D.4: <= 1e-5 relative to the tensor scale for
+activations, a few fp32 ulps of the coordinate for positions).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import contraction as OC
+from oracle import network as ON
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+ACT_TOL = 2e-5        # activations: max |gpu - oracle| / max |oracle| per tensor (fp32 FFMA, different summation order)
+POS_TOL = 4e-6        # contracted positions: absolute, metres, per coordinate of ~10 m magnitude (few ulps + pred error)
+DISP_TOL = 2e-5       # displacements: relative to max |displacement|
+
+
+def make_engine(state, **kw):
+    from smartqsm_b200._lib import Engine
+    eng = Engine(**kw)
+    eng.load_state_dict(state)
+    return eng
+
+
+def run_gpu_iteration(state, pts64, batch_size=16, disp=None, **kw):
+    eng = make_engine(state, batch_size=batch_size, **kw)
+    eng.debug_capture(True)
+    if disp is None:
+        eng.set_points(pts64)
+    else:
+        eng.set_state(pts64.astype(np.float32), disp)
+    st = eng.contract_step()
+    return eng, st
+
+
+def check_iteration(state, pts64, batch_size=16, disp=None, check_float=True):
+    p32 = pts64.astype(np.float32)
+    d32 = np.zeros_like(p32) if disp is None else disp.astype(np.float32)
+    w = ON.Weights(state)
+    Po, Do, tr = OC.contract_once(p32, d32, w, batch_size=batch_size, keep=True)
+    eng, st = run_gpu_iteration(state, pts64, batch_size, disp)
+
+    # ---- level-0 voxels in canonical order: coordinates, winners, interior mask (bit-exact)
+    o_idx = np.concatenate([np.concatenate([np.full((len(v.coords_zyx), 1), si, np.int32), v.coords_zyx], axis=1)
+                            for si, v in enumerate(tr.vox)])
+    o_win = np.concatenate([v.winner_global for v in tr.vox])
+    o_mask = np.concatenate([v.mask for v in tr.vox])
+    g_idx, g_win, g_mask = eng.debug_voxels()
+    assert st["n_vox"] == len(o_idx) and st["n_out"] == len(Po) and st["n_cubes"] == len(tr.samples)
+    assert np.array_equal(g_idx, o_idx), "voxel coordinates / order differ"
+    assert np.array_equal(g_win, o_win), "winning point per voxel differs"
+    assert np.array_equal(g_mask, o_mask), "interior mask differs"
+    assert st["far_face_rows"] == tr.far_face_rows
+
+    # ---- batch spatial shapes (max index, F6)
+    nb = len(tr.batches)
+    shp, desc = eng.debug_batch_shapes(nb)
+    assert np.array_equal(shp, np.stack([b.spatial_shape for b in tr.batches]).astype(np.int32))
+
+    # ---- rulebooks per level (compared through coordinates)
+    olv = H.oracle_level_tables(tr, batch_size)
+    g2o = []
+    n_levels = len(olv)
+    for l in range(n_levels):
+        assert eng.debug_level_size(l) == len(olv[l]["coords"]), f"level {l} row count"
+    for l in range(n_levels):
+        with_down = l + 1 < n_levels
+        gc, gn, gp, gk = eng.debug_level_tables(l, with_down)
+        m = H.match_rows(gc, olv[l]["coords"])
+        g2o.append(m)
+        inv = np.empty_like(m)
+        inv[m] = np.arange(len(m))
+        o_in_g = olv[l]["nbr"][:, m]                    # oracle table re-ordered to GPU rows, oracle numbering
+        assert np.array_equal(H.remap(gn, m), o_in_g), f"SubM rulebook differs at level {l}"
+    for l in range(n_levels - 1):
+        _, _, gp, gk = eng.debug_level_tables(l, True)
+        assert np.array_equal(H.remap(gp, g2o[l + 1]), olv[l]["parent"][g2o[l]]), f"parent table differs at level {l}"
+        acc = gp >= 0
+        assert np.array_equal(gk[acc], olv[l]["koff"][g2o[l]][acc]), f"kernel offsets differ at level {l}"
+        assert np.array_equal(desc[l].astype(bool), np.array(olv[l]["descended"])), f"descent flags differ at level {l}"
+    # level-0 canonical numbering is the oracle numbering
+    perm = eng.debug_canon_to_internal()
+    assert np.array_equal(g2o[0][perm], np.arange(len(perm)))
+
+    if not check_float:
+        return eng, st, (Po, Do, tr)
+    # ---- activations
+    names = ["input_conv"] + [f"enc{l}" for l in range(n_levels)] + [f"dec{l}" for l in range(n_levels - 1)]
+    for name in names:
+        g, lvl = eng.debug_features(name)
+        o = H.oracle_features(tr, name)
+        if name.startswith("dec"):
+            # the oracle only records `dec` for batches that descended; others keep `enc` (select in the kernel)
+            if not all(olv[lvl]["descended"]):
+                continue
+        assert g.shape == o.shape, (name, g.shape, o.shape)
+        err = H.rel_err(g, o[g2o[lvl]])
+        assert err <= ACT_TOL, f"{name}: relative error {err:.3e} > {ACT_TOL}"
+    # ---- heads
+    pred, off, reg = eng.debug_predictions()
+    o_off, o_reg = H.oracle_features(tr, "offset"), H.oracle_features(tr, "regression")
+    assert H.rel_err(off, o_off[g2o[0]]) <= 5e-5
+    assert H.rel_err(reg, o_reg[g2o[0]][:, 0]) <= 5e-5
+    # ---- iteration result: same rows, same order
+    Pg, Dg = eng.result()
+    assert Pg.shape == Po.shape
+    assert np.max(np.abs(Pg.astype(np.float64) - Po)) <= POS_TOL + 2e-5 * float(np.max(np.abs(Do)))
+    assert H.rel_err(Dg, Do) <= DISP_TOL
+    return eng, st, (Po, Do, tr)
+
+
+def test_single_iteration_real_weights(leafoff_state, small_tree):
+    check_iteration(leafoff_state, small_tree)
+
+
+def test_single_iteration_random_weights(random_state, small_tree):
+    check_iteration(random_state, small_tree)
+
+
+def test_ragged_batches(random_state):
+    """batch_size=3 on a tree that spans many cubes: several batches, the last one ragged."""
+    from smartqsm_b200.synthetic import make_tree
+    pts = make_tree(60000, 5)
+    eng, st, _ = check_iteration(random_state, pts, batch_size=3)
+    assert st["n_batches"] >= 3
+
+
+def test_second_iteration_from_oracle_state(leafoff_state, small_tree):
+    """App. D.4: integer parity of iteration t+1 is checked from the oracle's iteration-t floats."""
+    p32 = small_tree.astype(np.float32)
+    P1, D1, _ = OC.contract_once(p32, np.zeros_like(p32), ON.Weights(leafoff_state))
+    check_iteration(leafoff_state, P1.astype(np.float64), disp=D1)
+
+
+def test_face_points_and_tiny_batches(random_state):
+    """F11: points exactly on cube faces belong to two cubes; plus cubes with a single point whose
+    batch cannot descend (spatial_shape <= 2)."""
+    rng = np.random.default_rng(0)
+    a = rng.uniform(-1.0, 1.0, (4000, 3)) * np.array([3.0, 3.0, 3.0]) + np.array([0.0, 0.0, 3.0])
+    a[:200, 0] = 0.0                  # on the x = 0 face
+    a[200:300, 1] = 4.0               # on the y = 4 face (cube may or may not exist)
+    a[300:330, 2] = 4.0
+    far = np.array([[40.0, 40.0, 40.0], [80.5, 0.25, 0.25], [80.5, 0.25, 0.26]])
+    pts = np.concatenate([a, far])
+    for bs in (1, 16):
+        check_iteration(random_state, pts, batch_size=bs)
+
+
+def test_single_point(random_state):
+    pts = np.array([[0.123, 0.456, 0.789]])
+    eng, st, _ = check_iteration(random_state, pts)
+    assert st["n_vox"] == 1 and st["n_out"] == 1
+
+
+def test_full_run_with_chamfer_monitor(leafoff_state):
+    """10 thunks, monitor on, reference (non-latching) behaviour: same accept/reject sequence, same
+    sizes, same final state within tolerance."""
+    from smartqsm_b200.core_algorithms import SpconvBasedContraction
+    from smartqsm_b200.synthetic import make_tree
+    pts = make_tree(20000, 3)
+    o = OC.SpconvBasedContractionOracle(state=leafoff_state, monitored_by_chamfer_distance=True, max_iteration=10)
+    o.input(points=pts)
+    for f in o.get_pipeline():
+        f()
+    g = SpconvBasedContraction(state_dict=leafoff_state, batch_size=16, max_iteration=10, device="cuda",
+                               monitored_by_chamfer_distance=True)
+    g.input(points=pts)
+    pipe = g.get_pipeline()
+    assert len(pipe) == 10
+    for f in pipe:
+        assert f() is None
+    acc_o = [h["accepted"] for h in o.history]
+    acc_g = [bool(h["accepted"]) for h in g.history]
+    assert acc_o == acc_g
+    for ho, hg in zip(o.history, g.history):
+        assert abs(ho["n_out"] - hg["n_out"]) <= max(2, ho["n_out"] // 2000)       # sub-voxel float flips only
+        assert abs(ho["chamfer"] - hg["chamfer"]) <= 1e-6 * ho["chamfer"] + 1e-12 or ho["n_out"] != hg["n_out"]
+    out_o, out_g = o.output(), g.output()
+    if out_o["contracted_points"].shape == out_g["contracted_points"].shape:
+        assert np.max(np.abs(out_o["contracted_points"] - out_g["contracted_points"])) <= 1e-4
+    # downstream operators on the GPU state vs the oracle on the SAME state
+    ids_g, sk_g, rad_g = g.produce_skeletal_points_and_radii(0.01)
+    ids_o, sk_o, rad_o = OC.skeletal_points_and_radii(out_g["contracted_points"], out_g["displacements"], 0.01)
+    assert np.array_equal(ids_g, ids_o)
+    assert np.array_equal(sk_g, sk_o)
+    assert np.array_equal(rad_g, rad_o), "radii must be bit-exact (float32 sqrt of float32 sum of squares)"
+    e_g = g.radius_edges(0.055)
+    e_o = OC.radius_edges(sk_o, 0.055)
+    assert np.array_equal(e_g, e_o)
+
+
+def test_latched_run_matches_unlatched(leafoff_state):
+    from smartqsm_b200.core_algorithms import SpconvBasedContraction
+    from smartqsm_b200.synthetic import make_tree
+    pts = make_tree(20000, 4)
+    outs = []
+    for latch in (False, True):
+        g = SpconvBasedContraction(state_dict=leafoff_state, batch_size=16, max_iteration=10, device="cuda",
+                                   monitored_by_chamfer_distance=True, latch_early_stop=latch)
+        g.input(points=pts)
+        for f in g.get_pipeline():
+            f()
+        outs.append(g.output())
+    assert np.array_equal(outs[0]["contracted_points"], outs[1]["contracted_points"])
+    assert np.array_equal(outs[0]["displacements"], outs[1]["displacements"])
+
+
+def test_chamfer_value(leafoff_state, small_tree):
+    eng = make_engine(leafoff_state, monitored_by_chamfer_distance=True)
+    eng.set_points(small_tree)
+    st = eng.contract_step()
+    P1, _ = eng.result()
+    cd = OC.chamfer(small_tree.astype(np.float32), P1, 0.01)
+    assert abs(st["chamfer"] - cd) <= 1e-9 * cd        # float64 sums in a different order
+
+
+def test_radius_graph_points_and_boundaries():
+    """Closed ball in float64 (SciPy semantics) including exact-boundary pairs."""
+    from smartqsm_b200._lib import Engine
+    rng = np.random.default_rng(1)
+    pts = rng.uniform(0, 0.6, (6000, 3)).astype(np.float32)
+    # plant exact boundary pairs: distance exactly r along an axis in float32
+    r = 0.0625
+    pts[:50, :] = np.round(pts[:50, :] * 64) / 64
+    pts[50:100, :] = pts[:50, :] + np.array([r, 0, 0], np.float32)
+    eng = Engine()
+    e_g = eng.radius_graph_points(pts, r)
+    e_o = OC.radius_edges(pts, r)
+    assert np.array_equal(e_g, e_o)
+    e_g = eng.radius_graph_points(pts, 0.055)
+    assert np.array_equal(e_g, OC.radius_edges(pts, 0.055))
+    # empty / trivial inputs
+    assert eng.radius_graph_points(pts[:1], 0.055).shape == (0, 2)
+    far = np.array([[0, 0, 0], [10, 10, 10]], np.float32)
+    assert eng.radius_graph_points(far, 0.055).shape == (0, 2)
+
+
+def test_large_cloud_properties(random_state):
+    """Full-size properties (no oracle at this size): structural invariants of one iteration over a
+    1 M-point tree and bit-identical results when the same input is run twice (determinism: the
+    first-come rule is decided by atomicMin on indices, never by arrival order)."""
+    from smartqsm_b200.synthetic import make_tree
+    pts = make_tree(1_000_000, 21)
+    res = []
+    for _ in range(2):
+        eng = make_engine(random_state)
+        eng.debug_capture(True)
+        eng.set_points(pts)
+        st = eng.contract_step()
+        idx, win, mask = eng.debug_voxels()
+        P, D = eng.result()
+        res.append((st, idx, win, mask, P, D))
+    st0, idx0, win0, mask0, P0, D0 = res[0]
+    st1, idx1, win1, mask1, P1, D1 = res[1]
+    assert np.array_equal(idx0, idx1) and np.array_equal(win0, win1) and np.array_equal(mask0, mask1)
+    assert np.array_equal(P0, P1) and np.array_equal(D0, D1)
+    assert st0["n_vox"] == len(idx0) and st0["n_out"] == int(mask0.sum()) == len(P0)
+    assert np.all(np.isfinite(P0)) and np.all(np.isfinite(D0))
+    # canonical order: samples ascending, winners strictly ascending inside a sample, voxels unique
+    s = idx0[:, 0].astype(np.int64)
+    assert np.all(np.diff(s) >= 0)
+    same = np.diff(s) == 0
+    assert np.all(np.diff(win0)[same] > 0)
+    key = H.coord_key(idx0)
+    assert len(np.unique(key)) == len(key)
+    assert idx0[:, 1:].min() >= 0 and idx0[:, 1:].max() < 480
+    # every interior point of the input survives unless it shares a voxel: n_out <= n_in (+ face duplicates)
+    assert st0["n_out"] <= st0["n_in"] + 1000
