@@ -38,7 +38,11 @@ typedef struct SqsmConfig {
     int32_t latch_early_stop;           /* 1: remember a Chamfer rejection (fixes F10; results
                                            identical); 0: recompute like the reference does  */
     int32_t down_kernel_flip;           /* 0: k index = (z&1,y&1,x&1) (SURVEY App. A default) */
-    int32_t reserved[7];
+    int32_t conv_mode;                  /* arithmetic of the 16/32/64-channel convolutions:
+                                           0 = library default (2), 1 = fp32 FFMA everywhere,
+                                           2 = tcgen05 3xTF32 split (fp32-class accuracy),
+                                           3 = tcgen05 single-pass TF32 (reduced precision, App. D.4) */
+    int32_t reserved[6];
 } SqsmConfig;
 
 /* What one _contract() call did (spconv_based_contraction.py:75-140). */
@@ -133,12 +137,19 @@ int  sqsm_debug_features(sqsm_handle h, const char* stage, int32_t* level, int32
                          float* h_data, int64_t capacity);
 
 /* ---- measurement hooks ------------------------------------------------------------------ */
-/* device-time (CUDA events on the handle's stream) and launch count of one named kernel
- * family accumulated since the last reset; used by bench.py for roofline.achieved. */
+/* Kernel-family timing: CUDA events recorded on the handle's stream around every launch group of
+ * a family ("tiling", "voxelise", "rulebook", "subm_l0".."subm_l3", "down_up", "heads", "chamfer")
+ * while enabled; resolved lazily, so enabling it adds no synchronisation to a step.  Returns the
+ * accumulated device time, launch count, algorithmic bytes and FLOPs since the last reset. */
+int  sqsm_profile_enable(sqsm_handle h, int32_t enable);
 int  sqsm_profile_reset(sqsm_handle h);
 int  sqsm_profile_get(sqsm_handle h, const char* family, double* total_ms, int64_t* launches,
-                      double* algorithmic_bytes);
-int  sqsm_profile_enable(sqsm_handle h, int32_t enable);
+                      double* algorithmic_bytes, double* flops);
+int  sqsm_profile_families(sqsm_handle h, char* buf, int64_t capacity);   /* comma separated */
+/* Whole-step device timer: events on the handle's stream (torch's events only see torch's stream). */
+int  sqsm_timer_start(sqsm_handle h);
+int  sqsm_timer_stop(sqsm_handle h, double* elapsed_ms);
+int  sqsm_launch_count(sqsm_handle h, int64_t* kernels_launched_since_create);
 
 #ifdef __cplusplus
 }

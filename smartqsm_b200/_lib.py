@@ -20,7 +20,7 @@ class SqsmConfig(C.Structure):
         ("device", C.c_int32), ("batch_size", C.c_int32), ("max_iteration", C.c_int32),
         ("voxel_size", C.c_float), ("cube_size", C.c_float), ("buffer_size", C.c_float),
         ("monitored_by_chamfer_distance", C.c_int32), ("latch_early_stop", C.c_int32),
-        ("down_kernel_flip", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("down_kernel_flip", C.c_int32), ("conv_mode", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -47,7 +47,7 @@ EXPORTS = [
     "sqsm_radius_graph_points", "sqsm_debug_capture", "sqsm_debug_level_size", "sqsm_debug_voxels",
     "sqsm_debug_batch_shapes", "sqsm_debug_level_tables", "sqsm_debug_canon_to_internal",
     "sqsm_debug_predictions", "sqsm_debug_features", "sqsm_profile_reset", "sqsm_profile_get",
-    "sqsm_profile_enable",
+    "sqsm_profile_enable", "sqsm_profile_families", "sqsm_timer_start", "sqsm_timer_stop", "sqsm_launch_count",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -90,7 +90,11 @@ def load_library() -> C.CDLL:
         "sqsm_debug_predictions": ([vp, vp, vp, vp], C.c_int),
         "sqsm_debug_features": ([vp, cp, P(i32), P(i32), vp, i64], C.c_int),
         "sqsm_profile_reset": ([vp], C.c_int),
-        "sqsm_profile_get": ([vp, cp, P(f64), P(i64), P(f64)], C.c_int),
+        "sqsm_profile_get": ([vp, cp, P(f64), P(i64), P(f64), P(f64)], C.c_int),
+        "sqsm_profile_families": ([vp, vp, i64], C.c_int),
+        "sqsm_timer_start": ([vp], C.c_int),
+        "sqsm_timer_stop": ([vp, P(f64)], C.c_int),
+        "sqsm_launch_count": ([vp, P(i64)], C.c_int),
         "sqsm_profile_enable": ([vp, i32], C.c_int),
     }
     for name, (args, res) in sig.items():
@@ -109,12 +113,13 @@ class Engine:
 
     def __init__(self, *, device: int = 0, batch_size: int = 16, max_iteration: int = 10, voxel_size: float = 0.01,
                  cube_size: float = 4.0, buffer_size: float = 0.4, monitored_by_chamfer_distance: bool = False,
-                 latch_early_stop: bool = False, down_kernel_flip: bool = False) -> None:
+                 latch_early_stop: bool = False, down_kernel_flip: bool = False, conv_mode: int = 0) -> None:
         self._lib = load_library()
         cfg = SqsmConfig(device=device, batch_size=batch_size, max_iteration=max_iteration, voxel_size=voxel_size,
                          cube_size=cube_size, buffer_size=buffer_size,
                          monitored_by_chamfer_distance=int(monitored_by_chamfer_distance),
-                         latch_early_stop=int(latch_early_stop), down_kernel_flip=int(down_kernel_flip))
+                         latch_early_stop=int(latch_early_stop), down_kernel_flip=int(down_kernel_flip),
+                         conv_mode=int(conv_mode))
         h = C.c_void_p()
         rc = self._lib.sqsm_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -287,8 +292,27 @@ class Engine:
     def profile_reset(self) -> None:
         self._check(self._lib.sqsm_profile_reset(self._h), "profile_reset")
 
-    def profile_get(self, family: str):
-        ms, n, by = C.c_double(), C.c_int64(), C.c_double()
-        self._check(self._lib.sqsm_profile_get(self._h, family.encode(), C.byref(ms), C.byref(n), C.byref(by)),
-                    "profile_get")
-        return ms.value, n.value, by.value
+    def profile_get(self, family: str) -> dict:
+        ms, n, by, fl = C.c_double(), C.c_int64(), C.c_double(), C.c_double()
+        self._check(self._lib.sqsm_profile_get(self._h, family.encode(), C.byref(ms), C.byref(n), C.byref(by),
+                                               C.byref(fl)), "profile_get")
+        return {"ms": ms.value, "launches": n.value, "bytes": by.value, "flops": fl.value}
+
+    def profile_all(self) -> Dict[str, dict]:
+        buf = C.create_string_buffer(4096)
+        self._check(self._lib.sqsm_profile_families(self._h, buf, 4096), "profile_families")
+        names = [n for n in buf.value.decode().split(",") if n]
+        return {n: self.profile_get(n) for n in names}
+
+    def timer_start(self) -> None:
+        self._check(self._lib.sqsm_timer_start(self._h), "timer_start")
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        self._check(self._lib.sqsm_timer_stop(self._h, C.byref(ms)), "timer_stop")
+        return ms.value
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        self._check(self._lib.sqsm_launch_count(self._h, C.byref(n)), "launch_count")
+        return n.value

@@ -91,7 +91,7 @@ class SpconvBasedContraction(CoreAlgorithmBase):
     def __init__(self, *, ckpt_path: Optional[str] = None, batch_size: int, max_iteration: int, device: str = "cuda",
                  voxel_size: float = 0.01, cube_size: float = 4.0, buffer_size: float = 0.4, verbose: bool = False,
                  monitored_by_chamfer_distance: bool = False, state_dict: Optional[Dict[str, np.ndarray]] = None,
-                 latch_early_stop: Optional[bool] = None) -> None:
+                 latch_early_stop: Optional[bool] = None, conv_mode: int = 0) -> None:
         super().__init__(verbose=verbose)
         self._verbose = verbose
         self._max_iteration = max_iteration
@@ -103,7 +103,8 @@ class SpconvBasedContraction(CoreAlgorithmBase):
         latch = verbose if latch_early_stop is None else latch_early_stop
         self._engine = Engine(device=_device_ordinal(device), batch_size=batch_size, max_iteration=max_iteration,
                               voxel_size=voxel_size, cube_size=cube_size, buffer_size=buffer_size,
-                              monitored_by_chamfer_distance=monitored_by_chamfer_distance, latch_early_stop=latch)
+                              monitored_by_chamfer_distance=monitored_by_chamfer_distance, latch_early_stop=latch,
+                              conv_mode=conv_mode)
         if state_dict is None:
             if ckpt_path is None:
                 raise ValueError("ckpt_path (or state_dict) is required")

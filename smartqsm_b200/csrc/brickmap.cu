@@ -49,7 +49,7 @@ void sort_pairs_u32(Ctx& cx, const uint32_t* d_kin, uint32_t* d_kout, const uint
 
 // Insert every entry's brick key; the thread that claims a slot appends the key to the list.
 __global__ void __launch_bounds__(256) k_brick_insert(BrickHash h, const uint64_t* __restrict__ ent_key,
-                                                      int64_t n_ent, uint64_t* __restrict__ list,
+                                                      int64_t n_ent, uint64_t* __restrict__ list, int list_cap,
                                                       int32_t* __restrict__ counter) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_ent) return;
@@ -59,8 +59,12 @@ __global__ void __launch_bounds__(256) k_brick_insert(BrickHash h, const uint64_
     unsigned peers = __match_any_sync(__activemask(), key);
     if ((int)(__ffs(peers) - 1) != (int)(threadIdx.x & 31)) return;
     bool ins;
-    hash_insert(h, key, &ins);
-    if (ins) list[atomicAdd(counter, 1)] = key;
+    uint32_t slot = hash_insert(h, key, &ins);
+    if (slot == 0xFFFFFFFFu) { counter[1] = 1; return; }            // table too small: the host retries
+    if (ins) {
+        int idx = atomicAdd(counter, 1);
+        if (idx < list_cap) list[idx] = key; else counter[1] = 1;
+    }
 }
 
 // Brick i takes the i-th sorted key; publish the id in the hash.
@@ -157,24 +161,36 @@ static uint32_t next_pow2(uint64_t v) {
 void brickmap_build(Ctx& cx, BrickMap& m, const uint64_t* d_ent_key, const uint16_t* d_ent_pos, int64_t n_ent,
                     int32_t* d_ent_brick) {
     cudaStream_t st = cx.st;
+    Trace tr(cx, "  brickmap_build");
     SQSM_CHECK(n_ent < (1ll << 31), "too many entries for one BrickMap build");
     m.n_bricks = 0;
     m.n_rows = 0;
     if (n_ent == 0) return;
-    // <= 50 % load even if every entry opened its own brick
-    m.cap = next_pow2((uint64_t)n_ent * 2);
-    m.hkeys.alloc(m.cap, st);
-    m.hvals.alloc(m.cap, st);
-    m.hkeys.fill_ff();
-    DBuf<uint64_t> list(n_ent, st);
-    DBuf<int32_t> counter(1, st);
-    counter.zero();
+    // Expect far fewer bricks than entries (a brick holds up to 512 voxels): start with a table of about
+    // n_ent/2 slots (L2 resident for the sizes of this path) and retry with 4x if it exceeds 50 % load.
+    DBuf<uint64_t> list;
+    DBuf<int32_t> counter(2, st);
     int grid = div_up(n_ent, 256);
-    k_brick_insert<<<grid, 256, 0, st>>>(m.view(), d_ent_key, n_ent, list.p, counter.p);
-    cx.launches++;
     int32_t nb = 0;
-    SQSM_CUDA(cudaMemcpyAsync(&nb, counter.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    SQSM_CUDA(cudaStreamSynchronize(st));
+    uint64_t want = std::max<uint64_t>((uint64_t)n_ent / 2, 4096);
+    for (int attempt = 0;; ++attempt) {
+        m.cap = next_pow2(want);
+        const int list_cap = (int)std::min<uint64_t>((uint64_t)m.cap / 2, (uint64_t)n_ent);
+        m.hkeys.alloc(m.cap, st);
+        m.hvals.alloc(m.cap, st);
+        m.hkeys.fill_ff();
+        list.alloc(list_cap, st);
+        counter.zero();
+        k_brick_insert<<<grid, 256, 0, st>>>(m.view(), d_ent_key, n_ent, list.p, list_cap, counter.p);
+        cx.launches++;
+        int32_t hc[2];
+        SQSM_CUDA(cudaMemcpyAsync(hc, counter.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+        SQSM_CUDA(cudaStreamSynchronize(st));
+        nb = hc[0];
+        if (hc[1] == 0) break;
+        SQSM_CHECK(attempt < 4, "brick hash overflow");
+        want = (uint64_t)m.cap * 4;
+    }
     m.n_bricks = nb;
     if (nb == 0) return;
     DBuf<uint64_t> sorted(nb, st);

@@ -10,12 +10,58 @@
 // convolutions hit L2.
 #pragma once
 #include "common.cuh"
+#include <string>
+#include <stdlib.h>
+#include <time.h>
+#include <vector>
 
 namespace sqsm {
+
+struct ProfRec { cudaEvent_t a, b; int fam; int64_t launches; double bytes, flops; };
 
 struct Ctx {                       // per-engine launch context
     cudaStream_t st = nullptr;
     int64_t launches = 0;
+    bool prof_on = false;          // kernel-family timing (events are resolved lazily, no sync here)
+    std::vector<std::string> fam_names;
+    std::vector<ProfRec> pending;
+    int family(const std::string& name) {
+        for (size_t i = 0; i < fam_names.size(); ++i) if (fam_names[i] == name) return (int)i;
+        fam_names.push_back(name);
+        return (int)fam_names.size() - 1;
+    }
+};
+
+// RAII: CUDA events around a kernel family on the launching stream.
+struct ProfScope {
+    Ctx& cx; ProfRec r; bool on;
+    ProfScope(Ctx& c, const char* fam, double bytes, double flops) : cx(c), on(c.prof_on) {
+        if (!on) return;
+        r.fam = cx.family(fam); r.bytes = bytes; r.flops = flops; r.launches = cx.launches;
+        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, cx.st);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(r.b, cx.st);
+        r.launches = cx.launches - r.launches;
+        cx.pending.push_back(r);
+    }
+};
+
+// SQSM_TRACE=1: host wall-clock per stage, with and without draining the stream (finds host stalls)
+struct Trace {
+    Ctx& cx; const char* name; double t0; bool on;
+    static bool enabled() { static int e = -1; if (e < 0) { const char* v = getenv("SQSM_TRACE"); e = (v && v[0] == '1') ? 1 : 0; } return e == 1; }
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    Trace(Ctx& c, const char* n) : cx(c), name(n), on(enabled()) { if (on) { cudaStreamSynchronize(cx.st); t0 = now(); } }
+    ~Trace() {
+        if (!on) return;
+        double t1 = now();
+        cudaStreamSynchronize(cx.st);
+        double t2 = now();
+        fprintf(stderr, "[trace] %-22s host %8.3f ms  +drain %8.3f ms\n", name, t1 - t0, t2 - t1);
+    }
 };
 
 struct BrickMap {

@@ -231,6 +231,8 @@ __global__ void __launch_bounds__(256) k_heads(const float* __restrict__ feat, c
 
 // ---------------------------------------------------------------------------------- weights
 
+std::vector<float> make_tc_weight_image(const float* w_kcico, int kv, int ci, int co);   // conv_tc.cu
+
 static const std::vector<float>& need(const std::map<std::string, std::vector<float>>& st, const std::string& k,
                                       size_t n) {
     auto it = st.find(k);
@@ -256,12 +258,12 @@ static void fold_bn(const std::map<std::string, std::vector<float>>& st, const s
 
 void net_upload(Ctx& cx, NetWeights& nw, const std::map<std::string, std::vector<float>>& st, bool down_flip) {
     std::vector<float> blob;
-    struct Pending { std::string name; size_t w_off, bn_off; bool has_bn; int ci, co, kv; };
+    struct Pending { std::string name; size_t w_off, bn_off, img_off; bool has_bn, has_img; int ci, co, kv; };
     std::vector<Pending> pend;
     auto add_conv = [&](const std::string& name, const std::string& wkey, const std::string& bnkey, int ci, int co, int kv,
                         int ci_pad, bool flip) {
         const auto& W = need(st, wkey, (size_t)co * kv * ci);   // [co][k][ci]
-        Pending p{name, blob.size(), 0, !bnkey.empty(), ci_pad, co, kv};
+        Pending p{name, blob.size(), 0, 0, !bnkey.empty(), false, ci_pad, co, kv};
         blob.resize(blob.size() + (size_t)kv * ci_pad * co, 0.0f);
         for (int k = 0; k < kv; ++k)
             for (int c = 0; c < ci; ++c)
@@ -275,6 +277,13 @@ void net_upload(Ctx& cx, NetWeights& nw, const std::map<std::string, std::vector
             fold_bn(st, bnkey, ci, &blob[p.bn_off], &blob[p.bn_off + ci_pad]);
         }
         while (blob.size() % 4) blob.push_back(0.0f);
+        if (ci_pad % 8 == 0 && co <= 64) {                      // tensor-core weight image (conv_tc.cu)
+            std::vector<float> img = make_tc_weight_image(&blob[p.w_off], kv, ci_pad, co);
+            while (blob.size() % 64) blob.push_back(0.0f);      // 256-byte aligned
+            p.img_off = blob.size();
+            p.has_img = true;
+            blob.insert(blob.end(), img.begin(), img.end());
+        }
         pend.push_back(p);
     };
     add_conv("input", "input_conv.0.weight", "", 3, kPlanes[0], 27, 4, false);
@@ -303,6 +312,7 @@ void net_upload(Ctx& cx, NetWeights& nw, const std::map<std::string, std::vector
         c.ci = p.ci; c.co = p.co; c.kv = p.kv;
         c.w = nw.blob.p + p.w_off;
         c.bn = p.has_bn ? nw.blob.p + p.bn_off : nullptr;
+        c.wimg = p.has_img ? nw.blob.p + p.img_off : nullptr;
         nw.conv[p.name] = c;
     }
     // heads (App. A #48-51)
@@ -327,30 +337,6 @@ void net_upload(Ctx& cx, NetWeights& nw, const std::map<std::string, std::vector
 
 // ---------------------------------------------------------------------------------- forward
 
-struct ProfTimer {
-    cudaEvent_t a = nullptr, b = nullptr;
-    std::map<std::string, ConvProfile>* prof;
-    std::string fam;
-    cudaStream_t st;
-    double bytes, flops;
-    int64_t l0;
-    Ctx& cx;
-    ProfTimer(Ctx& cx_, std::map<std::string, ConvProfile>* p, const std::string& f, double by, double fl)
-        : prof(p), fam(f), st(cx_.st), bytes(by), flops(fl), l0(cx_.launches), cx(cx_) {
-        if (prof) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
-    }
-    ~ProfTimer() {
-        if (!prof) return;
-        cudaEventRecord(b, st);
-        cudaEventSynchronize(b);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, a, b);
-        ConvProfile& c = (*prof)[fam];
-        c.ms += ms; c.launches += cx.launches - l0; c.bytes += bytes; c.flops += flops;
-        cudaEventDestroy(a); cudaEventDestroy(b);
-    }
-};
-
 template <int CI, int CO, int KV, bool BN, bool CAT>
 static void conv_dispatch(Ctx& cx, const ConvArgs& a) {
     if constexpr (CO == 8)       launch_conv<CI, CO, KV, 2, 8, BN, CAT>(cx, a);
@@ -358,36 +344,60 @@ static void conv_dispatch(Ctx& cx, const ConvArgs& a) {
     else                         launch_conv<CI, CO, KV, 4, 16, BN, CAT>(cx, a);
 }
 
-static ConvArgs mk(const ConvW& w, const float* inA, const float* inB, const int32_t* nbr, float* out, int64_t n_out,
-                   const float* res = nullptr, const float* sel_src = nullptr, const uint8_t* sel_flag = nullptr) {
-    ConvArgs a;
-    a.inA = inA; a.inB = inB; a.nbr = nbr; a.w = w.w; a.bn = w.bn; a.res = res; a.sel_src = sel_src;
-    a.sel_flag = sel_flag; a.out = out; a.n_out = (int)n_out; a.kc = 0;
-    return a;
+// conv_tc.cu
+bool conv_tc(Ctx& cx, int ci, int co, int kv, bool cat, const float* inA, const float* inB, const float* inA_lo,
+             const float* inB_lo, const int32_t* nbr, const float* wimg, const float* res, const float* sel_src,
+             const uint8_t* sel_flag, float* out, int64_t n_out, bool precise);
+void act_split(Ctx& cx, const float* in, const float* bn, int c, int bn_off, int bn_stride, int64_t n, float* hi, float* lo);
+
+static bool conv_ffma(Ctx& cx, const ConvW& w, bool cat, const ConvArgs& a) {
+    const bool bn = w.bn != nullptr;
+#define SQSM_FF_CASE(CI_, CO_, KV_, BN_, CAT_)                                                    \
+    if (w.ci == CI_ && w.co == CO_ && w.kv == KV_ && bn == BN_ && cat == CAT_) {                  \
+        conv_dispatch<CI_, CO_, KV_, BN_, CAT_>(cx, a);                                           \
+        return true;                                                                              \
+    }
+    SQSM_FF_CASE(4, 8, 27, false, false)
+    SQSM_FF_CASE(8, 8, 27, true, false) SQSM_FF_CASE(16, 16, 27, true, false) SQSM_FF_CASE(32, 32, 27, true, false)
+    SQSM_FF_CASE(64, 64, 27, true, false)
+    SQSM_FF_CASE(16, 8, 27, true, true) SQSM_FF_CASE(32, 16, 27, true, true) SQSM_FF_CASE(64, 32, 27, true, true)
+    SQSM_FF_CASE(16, 8, 1, false, true) SQSM_FF_CASE(32, 16, 1, false, true) SQSM_FF_CASE(64, 32, 1, false, true)
+    SQSM_FF_CASE(8, 16, 8, true, false) SQSM_FF_CASE(16, 32, 8, true, false) SQSM_FF_CASE(32, 64, 8, true, false)
+    SQSM_FF_CASE(16, 8, 8, true, false) SQSM_FF_CASE(32, 16, 8, true, false) SQSM_FF_CASE(64, 32, 8, true, false)
+#undef SQSM_FF_CASE
+    return false;
 }
 
-template <int C>
-static void run_block(Ctx& cx, const NetWeights& nw, const std::string& L, const LevelTables& lv, const float* x,
-                      float* tmp, float* out, std::map<std::string, ConvProfile>* prof, int level) {
-    // ResidualBlock with identity i_branch (sparse_module.py:32-39): out = convB(bnrelu(convA(bnrelu(x)))) + x
-    double by = 2.0 * (4.0 * lv.n * C * 2 + 4.0 * 27 * lv.n) + 4.0 * lv.n * C;
-    ProfTimer pt(cx, prof, "subm_l" + std::to_string(level), by, 2.0 * 2.0 * (double)lv.pairs * C * C);
-    conv_dispatch<C, C, 27, true, false>(cx, mk(nw.conv.at(L + ".blk.a"), x, nullptr, lv.nbr.p, tmp, lv.n));
-    conv_dispatch<C, C, 27, true, false>(cx, mk(nw.conv.at(L + ".blk.b"), tmp, nullptr, lv.nbr.p, out, lv.n, x));
+// One convolution of the network: tensor-core path for C_out >= 16 (inputs pre-activated once), FFMA otherwise.
+static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, bool cat, const float* inA, const float* inB,
+                     const int32_t* nbr, float* out, int64_t n_out, int64_t n_in, const float* res = nullptr,
+                     const float* sel_src = nullptr, const uint8_t* sel_flag = nullptr) {
+    const ConvW& w = nw.conv.at(name);
+    if (n_out <= 0) return;
+    if (nw.mode != 0 && w.wimg && w.co >= nw.tc_min_co) {
+        // activation + TF32 hi/lo split once per element, then the tensor-core implicit GEMM
+        const bool precise = nw.mode == 1;
+        const int ca = cat ? w.ci / 2 : w.ci;
+        DBuf<float> a_hi(n_in * ca, cx.st), a_lo, b_hi, b_lo;
+        if (precise) a_lo.alloc(n_in * ca, cx.st);
+        act_split(cx, inA, w.bn, ca, 0, w.ci, n_in, a_hi.p, a_lo.p);
+        if (cat) {
+            b_hi.alloc(n_in * ca, cx.st);
+            if (precise) b_lo.alloc(n_in * ca, cx.st);
+            act_split(cx, inB, w.bn, ca, ca, w.ci, n_in, b_hi.p, b_lo.p);
+        }
+        if (conv_tc(cx, w.ci, w.co, w.kv, cat, a_hi.p, b_hi.p, a_lo.p, b_lo.p, nbr, w.wimg, res, sel_src, sel_flag, out, n_out,
+                    precise))
+            return;
+    }
+    ConvArgs ar;
+    ar.inA = inA; ar.inB = inB; ar.nbr = nbr; ar.w = w.w; ar.bn = w.bn; ar.res = res; ar.sel_src = sel_src;
+    ar.sel_flag = sel_flag; ar.out = out; ar.n_out = (int)n_out; ar.kc = 0;
+    if (!conv_ffma(cx, w, cat, ar)) throw CudaError("no convolution kernel for layer " + name);
 }
 
-template <int C>
-static void run_tail(Ctx& cx, const NetWeights& nw, const std::string& L, const LevelTables& lv, const float* enc,
-                     const float* up, float* res, float* tmp, float* out, std::map<std::string, ConvProfile>* prof,
-                     int level) {
-    // blocks_tail on cat(enc, up) (sparse_module.py:114-116); rows of batches that did not descend keep `enc`
-    double by = 4.0 * lv.n * (2 * C + C) * 2 + 4.0 * lv.n * (C + C) + 2.0 * 4.0 * 27 * lv.n + 4.0 * lv.n * C;
-    ProfTimer pt(cx, prof, "subm_l" + std::to_string(level), by,
-                 2.0 * (double)lv.pairs * (2 * C * C + C * C) + 2.0 * (double)lv.n * 2 * C * C);
-    conv_dispatch<2 * C, C, 1, false, true>(cx, mk(nw.conv.at(L + ".tail.i"), enc, up, nullptr, res, lv.n));
-    conv_dispatch<2 * C, C, 27, true, true>(cx, mk(nw.conv.at(L + ".tail.a"), enc, up, lv.nbr.p, tmp, lv.n));
-    conv_dispatch<C, C, 27, true, false>(cx, mk(nw.conv.at(L + ".tail.b"), tmp, nullptr, lv.nbr.p, out, lv.n, res, enc,
-                                                lv.row_desc.p));
+static const char* lvl_family(int level) {
+    return level == 0 ? "subm_l0" : level == 1 ? "subm_l1" : level == 2 ? "subm_l2" : "subm_l3";
 }
 
 static void keep_copy(Ctx& cx, ForwardBuffers& fb, const std::string& name, const float* src, int64_t n, int ch,
@@ -399,69 +409,58 @@ static void keep_copy(Ctx& cx, ForwardBuffers& fb, const std::string& name, cons
 }
 
 void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Rows& rows, int n_levels,
-                 ForwardBuffers& fb, bool keep, float* d_newP, float* d_newD,
-                 std::map<std::string, ConvProfile>* prof) {
+                 ForwardBuffers& fb, bool keep, float* d_newP, float* d_newD) {
     cudaStream_t st = cx.st;
     SQSM_CHECK(nw.ready, "weights not finalised");
     DBuf<float> enc[kLevels], tmp[kLevels];
-    // ---- encoder
+    // ---- encoder (smart_tree_xx.py:65-66, sparse_module.py:101-112)
     const int64_t n0 = lv[0].n;
-    DBuf<float> x0(n0 * 8, st);
+    DBuf<float> cur_in(n0 * 8, st);
     {
-        ProfTimer pt(cx, prof, "subm_l0", 4.0 * n0 * (3 + 8) + 4.0 * 27 * n0, 2.0 * (double)lv[0].pairs * 3 * 8);
-        conv_dispatch<4, 8, 27, false, false>(cx, mk(nw.conv.at("input"), (const float*)rows.xyz.p, nullptr, lv[0].nbr.p,
-                                                     x0.p, n0));
+        ProfScope pt(cx, "subm_l0", 4.0 * n0 * (3 + 8) + 4.0 * 27 * n0, 2.0 * (double)lv[0].pairs * 3 * 8);
+        conv_any(cx, nw, "input", false, (const float*)rows.xyz.p, nullptr, lv[0].nbr.p, cur_in.p, n0, n0);
     }
-    if (keep) keep_copy(cx, fb, "input_conv", x0.p, n0, 8, 0);
-    DBuf<float> cur_in = std::move(x0);
+    if (keep) keep_copy(cx, fb, "input_conv", cur_in.p, n0, 8, 0);
     for (int l = 0; l < n_levels; ++l) {
         const int64_t n = lv[l].n;
         const int c = kPlanes[l];
-        std::string L = "L" + std::to_string(l);
+        const std::string L = "L" + std::to_string(l);
         enc[l].alloc(n * c, st);
         tmp[l].alloc(n * c, st);
-        switch (l) {
-            case 0: run_block<8>(cx, nw, L, lv[l], cur_in.p, tmp[l].p, enc[l].p, prof, l); break;
-            case 1: run_block<16>(cx, nw, L, lv[l], cur_in.p, tmp[l].p, enc[l].p, prof, l); break;
-            case 2: run_block<32>(cx, nw, L, lv[l], cur_in.p, tmp[l].p, enc[l].p, prof, l); break;
-            default: run_block<64>(cx, nw, L, lv[l], cur_in.p, tmp[l].p, enc[l].p, prof, l); break;
+        {   // ResidualBlock with identity i_branch (sparse_module.py:32-39): out = convB(bnrelu(convA(bnrelu(x)))) + x
+            ProfScope pt(cx, lvl_family(l), 2.0 * (4.0 * n * c * 2 + 4.0 * 27 * n) + 4.0 * n * c,
+                         2.0 * 2.0 * (double)lv[l].pairs * c * c);
+            conv_any(cx, nw, L + ".blk.a", false, cur_in.p, nullptr, lv[l].nbr.p, tmp[l].p, n, n);
+            conv_any(cx, nw, L + ".blk.b", false, tmp[l].p, nullptr, lv[l].nbr.p, enc[l].p, n, n, cur_in.p);
         }
         if (keep) keep_copy(cx, fb, "enc" + std::to_string(l), enc[l].p, n, c, l);
         if (l + 1 < n_levels) {
             const int64_t nn = lv[l + 1].n;
             DBuf<float> nxt(nn * kPlanes[l + 1], st);
-            ProfTimer pt(cx, prof, "down_up", 4.0 * (n * c + nn * kPlanes[l + 1]) + 4.0 * n,
-                         2.0 * (double)n * c * kPlanes[l + 1]);
-            ConvArgs a = mk(nw.conv.at(L + ".down"), enc[l].p, nullptr, lv[l].child.p, nxt.p, nn);
-            switch (l) {
-                case 0: conv_dispatch<8, 16, 8, true, false>(cx, a); break;
-                case 1: conv_dispatch<16, 32, 8, true, false>(cx, a); break;
-                default: conv_dispatch<32, 64, 8, true, false>(cx, a); break;
-            }
+            ProfScope pt(cx, "down_up", 4.0 * (n * c + nn * kPlanes[l + 1]) + 4.0 * n, 2.0 * (double)n * c * kPlanes[l + 1]);
+            conv_any(cx, nw, L + ".down", false, enc[l].p, nullptr, lv[l].child.p, nxt.p, nn, n);
             cur_in = std::move(nxt);
         }
     }
-    // ---- decoder
+    // ---- decoder (sparse_module.py:112-116)
     DBuf<float> cur = std::move(enc[n_levels - 1]);
     for (int l = n_levels - 2; l >= 0; --l) {
         const int64_t n = lv[l].n;
         const int c = kPlanes[l];
-        std::string L = "L" + std::to_string(l);
+        const std::string L = "L" + std::to_string(l);
         DBuf<float> up(n * c, st), res(n * c, st), out(n * c, st);
         {
-            ProfTimer pt(cx, prof, "down_up", 4.0 * (lv[l + 1].n * kPlanes[l + 1] + n * c) + 4.0 * n,
+            ProfScope pt(cx, "down_up", 4.0 * (lv[l + 1].n * kPlanes[l + 1] + n * c) + 4.0 * n,
                          2.0 * (double)n * c * kPlanes[l + 1]);
-            ConvArgs a = mk(nw.conv.at(L + ".up"), cur.p, nullptr, lv[l].inv.p, up.p, n);
-            switch (l) {
-                case 0: conv_dispatch<16, 8, 8, true, false>(cx, a); break;
-                case 1: conv_dispatch<32, 16, 8, true, false>(cx, a); break;
-                default: conv_dispatch<64, 32, 8, true, false>(cx, a); break;
-            }
+            conv_any(cx, nw, L + ".up", false, cur.p, nullptr, lv[l].inv.p, up.p, n, lv[l + 1].n);
         }
-        switch (l) {
-            case 0: run_tail<8>(cx, nw, L, lv[l], enc[l].p, up.p, res.p, tmp[l].p, out.p, prof, l); break;
-            case 1: run_tail<16>(cx, nw, L, lv[l], enc[l].p, up.p, res.p, tmp[l].p, out.p, prof, l); break;
-            default: run_tail<32>(cx, nw, L, lv[l], enc[l].p, up.p, res.p, tmp[l].p, out.p, prof, l); break;
+        {   // blocks_tail on cat(enc, up); rows of batches that did not descend keep `enc`
+            ProfScope pt(cx, lvl_family(l), 4.0 * n * (2 * c + c) * 2 + 4.0 * n * (c + c) + 2.0 * 4.0 * 27 * n + 4.0 * n * c,
+                         2.0 * (double)lv[l].pairs * (2 * c * c + c * c) + 2.0 * (double)n * 2 * c * c);
+            conv_any(cx, nw, L + ".tail.i", true, enc[l].p, up.p, nullptr, res.p, n, n);
+            conv_any(cx, nw, L + ".tail.a", true, enc[l].p, up.p, lv[l].nbr.p, tmp[l].p, n, n);
+            conv_any(cx, nw, L + ".tail.b", false, tmp[l].p, nullptr, lv[l].nbr.p, out.p, n, n, res.p, enc[l].p,
+                     lv[l].row_desc.p);
         }
         if (keep) keep_copy(cx, fb, "dec" + std::to_string(l), out.p, n, c, l);
         cur = std::move(out);
@@ -472,7 +471,7 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
         fb.offset.alloc(n0 * 4, st);
     }
     {
-        ProfTimer pt(cx, prof, "heads", (double)n0 * (32 + 32 + 4 + 24), 2.0 * (double)n0 * 2 * (64 + 32 + 12));
+        ProfScope pt(cx, "heads", (double)n0 * (32 + 32 + 4 + 24), 2.0 * (double)n0 * 2 * (64 + 32 + 12));
         HeadParams hp;
         hp.w = nw.head;
         k_heads<<<div_up(n0, 256), 256, 0, st>>>(cur.p, nullptr, nullptr, rows.xyz.p, rows.disp.p, rows.out.p, (int)n0, hp,

@@ -1,0 +1,418 @@
+// Tensor-core sparse convolution: implicit GEMM on tcgen05 (5th-gen tensor cores, TMEM accumulators).
+// sm_100a only.
+//
+// Every sparse convolution of the U-Net is a GEMM  D[rows, C_out] = A[rows, KV*C_in] . W[KV*C_in, C_out]
+// whose A operand is gathered through the output-stationary rulebook (nbr[k][row] = input row or -1,
+// zero when absent).  For C >= 16 the fp32 FFMA pipe is the bound of the SIMT kernel in conv.cu, so the
+// 16/32/64-channel layers run here instead:
+//
+//   * a persistent CTA per SM walks tiles of 128 output rows;
+//   * the activated input is split once per element into TF32 "hi" and "lo" arrays (k_act_split);
+//   * 128 producer threads gather the K dimension in chunks of 32 floats (128 B per row) with cp.async
+//     (LDGSTS, 16 B, zero-fill for absent neighbours) straight into two SWIZZLE_128B K-major shared-memory
+//     tiles (hi, lo); the matching weight chunk (pre-split, pre-swizzled on the host) is copied next to
+//     them; completion is tracked by cp.async.mbarrier.arrive, so a ring of STAGES chunks is in flight
+//     without holding registers or scoreboard slots (a register-staged gather stalls in order on the
+//     dependent rulebook -> row loads; measured in profiles/);
+//   * one thread issues tcgen05.mma.kind::tf32 (M=128, N=C_out, K=8) three times per 32-byte K step
+//     (hi*hi + lo*hi + hi*lo: "3xTF32", error ~2^-22 per product, i.e. fp32-class accuracy; the reduced
+//     single-pass mode of App. D.4 is a template switch) accumulating in TMEM, and releases the stage with
+//     tcgen05.commit;
+//   * the producer threads then become the epilogue: tcgen05.ld their accumulator row from TMEM, add the
+//     residual, apply the "batch did not descend" select and store the row.
+//
+// TMA is not used for A: the rows of a tile come from arbitrary addresses (a gather), which is exactly
+// what TMA cannot express; the weight chunk is small and shared by all tiles (L2 resident).
+#include "engine.h"
+#include <cstring>
+
+namespace sqsm {
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] . B[smem desc], kind::tf32, issued by ONE thread for the CTA
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrives when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 lanes x 16 consecutive 32-bit columns of TMEM -> 16 registers per thread
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    #pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 16-byte asynchronous global->shared copy; src_bytes = 0 writes zeros (absent neighbour)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one arrival from this thread once all its prior cp.async have landed
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// round-to-nearest TF32 (low 13 mantissa bits cleared).  Rounding (not truncating) both the "hi" part and the
+// remainder keeps the 3xTF32 error unbiased, so it grows like sqrt(K) instead of K.
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100 version 1):
+// rows of 128 B, groups of 8 rows 1024 B apart (SBO), LBO unused (1), 16-byte chunks XOR-swizzled by row&7.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+
+struct TcArgs {
+    const float* inA;         // [n_in][CI] TF32 hi part of the activated input (or first CI/2 channels when CAT)
+    const float* inB;         // hi part of the second CI/2 channels when CAT
+    const float* inA_lo;      // matching lo parts (PRECISE)
+    const float* inB_lo;
+    const int32_t* nbr;       // [KV][n_out] or nullptr (identity, KV == 1)
+    const float* wimg;        // per chunk: hi tile [NP][32] then lo tile [NP][32], SWIZZLE_128B images
+    const float* res;         // [n_out][CO] or nullptr
+    const float* sel_src;     // [n_out][CO] or nullptr
+    const uint8_t* sel_flag;
+    float* out;               // [n_out][CO]
+    int n_out;
+    int n_tiles;
+};
+
+constexpr int kTcStages = 4;          // shared-memory ring (A hi/lo + B hi/lo per stage)
+constexpr int kTcPrefetch = 3;        // chunks of gather loads in flight per producer thread (registers)
+constexpr int kTcProducers = 128;     // warps 0-3: gather; thread t owns tile row t
+constexpr int kTcEpilogue = 128;      // warps 4-7: TMEM -> registers -> global; thread owns tile row t-128
+constexpr int kTcThreads = kTcProducers + kTcEpilogue + 32;   // warp 8: MMA issuer
+constexpr uint32_t kTmemCols = 128;   // two accumulator stages of 64 columns
+
+template <int CI, int CO, int KV, bool CAT, bool PRECISE>
+__global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant__ TcArgs a) {
+    constexpr int KT = KV * CI;                       // GEMM K
+    constexpr int NCH = (KT + 31) / 32;               // chunks of 32 floats
+    constexpr int NP = CO < 16 ? 16 : CO;             // UMMA N (M=128 needs N % 16 == 0)
+    constexpr int A_BYTES = 128 * 128;
+    constexpr int B_BYTES = NP * 128;
+    constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    static_assert(CI % 8 == 0 && NP <= 64 && B_BYTES % 1024 == 0, "tile shape");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B needs 1024 B alignment
+    __shared__ __align__(8) uint64_t bars[2 * kTcStages + 4];
+    __shared__ uint32_t tmem_slot;
+
+    const int t = threadIdx.x;
+    const int warp = t >> 5;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kTcStages]);
+    const uint32_t tfull0 = smem_u32(&bars[2 * kTcStages]), tempty0 = smem_u32(&bars[2 * kTcStages + 2]);
+
+    if (t == 0) {
+        for (int s = 0; s < kTcStages; ++s) { mbar_init(full0 + 8 * s, kTcProducers); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, kTcEpilogue); }
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(smem_u32(&tmem_slot), kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp < 4) {
+        // ===================== producers: gather -> TF32 hi/lo split -> swizzled smem tiles =====================
+        // One chunk = 8 float4 per thread.  kTcPrefetch chunks are kept in flight in registers so that the
+        // latency of the gather (L2 / HBM) overlaps with the stores of earlier chunks.
+        const int n_my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int total = n_my_tiles * NCH;               // chunk sequence of this CTA
+        // Lane l of a warp copies piece (l & 7) of tile rows (l >> 3) + 4m, m = 0..7: the eight lanes of a row
+        // move one contiguous 128 B (or 2 x 64 B) span.  Rulebook entries are loaded by the lane that owns the
+        // row, RI-1 chunks ahead (the only register loads left), and travel by shuffle.
+        constexpr int KPC = (CI >= 32) ? 1 : 32 / CI;    // kernel offsets covered by one chunk
+        constexpr int RI = 4;
+        const int lane = t & 31;
+        const int piece = lane & 7;
+        const uint32_t smem_base = smem_u32(smem);
+        int ibuf[RI][KPC];
+        auto issue_idx = [&](int c, int* nb) {
+            const int tile = (int)blockIdx.x + (c / NCH) * (int)gridDim.x;
+            const int j = c % NCH;
+            const int row = tile * 128 + t;
+            #pragma unroll
+            for (int q = 0; q < KPC; ++q) {
+                const int k = (j * 32) / CI + q;
+                int n = -1;
+                if (row < a.n_out && k < KV) n = a.nbr ? __ldg(a.nbr + (size_t)k * a.n_out + row) : row;
+                nb[q] = n;
+            }
+        };
+        #pragma unroll
+        for (int d = 0; d < RI - 1; ++d)
+            if (d < total) issue_idx(d, ibuf[d]);
+        for (int c0 = 0; c0 < total; c0 += RI) {
+            #pragma unroll
+            for (int u = 0; u < RI; ++u) {
+                const int c = c0 + u;
+                if (c < total) {
+                    const uint32_t stage = (uint32_t)c % kTcStages, ph = ((uint32_t)c / kTcStages) & 1u;
+                    const int j = c % NCH;
+                    const uint32_t sA_hi = smem_base + stage * STAGE_BYTES;
+                    const uint32_t sA_lo = sA_hi + A_BYTES;
+                    const uint32_t sB = sA_lo + A_BYTES;
+                    const int idx = j * 32 + piece * 4;
+                    const int ci = idx % CI;
+                    mbar_wait(empty0 + 8 * stage, ph ^ 1u);
+                    #pragma unroll
+                    for (int m = 0; m < 8; ++m) {
+                        const int rl = (lane >> 3) + 4 * m;              // row inside this warp's 32 rows
+                        int n = -1;
+                        #pragma unroll
+                        for (int q = 0; q < KPC; ++q) {
+                            const int nq = __shfl_sync(0xFFFFFFFFu, ibuf[u][q], rl);
+                            if (KPC == 1 || (piece * 4) / CI == q) n = nq;
+                        }
+                        const bool on = (n >= 0) && (idx < KT);
+                        const size_t nn = on ? (size_t)n : 0;
+                        size_t eoff;
+                        bool second = false;
+                        if (CAT) { second = ci >= CI / 2; eoff = nn * (CI / 2) + (second ? ci - CI / 2 : ci); }
+                        else eoff = nn * CI + ci;
+                        const uint32_t rt = (uint32_t)(t & ~31) + (uint32_t)rl;
+                        const uint32_t off = rt * 128u + (uint32_t)((piece ^ (int)(rt & 7u)) << 4);
+                        const uint32_t sz = on ? 16u : 0u;
+                        cp_async16(sA_hi + off, (second ? a.inB : a.inA) + eoff, sz);
+                        if (PRECISE) cp_async16(sA_lo + off, (second ? a.inB_lo : a.inA_lo) + eoff, sz);
+                    }
+                    {   // weight chunk: hi tile then lo tile, already swizzled images (L2 resident)
+                        const float* src = a.wimg + (size_t)j * (2 * B_BYTES / 4);
+                        constexpr int NPIECE = (PRECISE ? 2 : 1) * B_BYTES / 16;
+                        #pragma unroll
+                        for (int i = 0; i < (NPIECE + kTcProducers - 1) / kTcProducers; ++i) {
+                            int q = t + i * kTcProducers;
+                            if (q < NPIECE) cp_async16(sB + 16u * q, src + 4 * q, 16u);
+                        }
+                    }
+                    cp_async_arrive(full0 + 8 * stage);   // one of the 128 arrivals, fires when this thread's copies landed
+                    if (c + RI - 1 < total) issue_idx(c + RI - 1, ibuf[(u + RI - 1) % RI]);
+                }
+            }
+        }
+    } else if (warp < 8) {
+        // ===================== epilogue: TMEM -> registers -> residual / select -> global =====================
+        const int te = t - kTcProducers;                  // tile row, also the TMEM lane
+        uint32_t tile_it = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tile_it) {
+            const uint32_t as = tile_it & 1u, aph = (tile_it >> 1) & 1u;
+            const int row = tile * 128 + te;
+            const bool live = row < a.n_out;
+            mbar_wait(tfull0 + 8 * as, aph);
+            tc_fence_after();
+            float acc[NP];
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + as * 64u;
+            #pragma unroll
+            for (int c = 0; c < NP; c += 16) tmem_ld16(taddr + c, acc + c);
+            tc_fence_before();
+            mbar_arrive(tempty0 + 8 * as);              // this accumulator stage may be overwritten
+            if (live) {
+                const size_t o = (size_t)row * CO;
+                const bool take_src = a.sel_flag && a.sel_flag[row] == 0;
+                #pragma unroll
+                for (int c = 0; c < CO; c += 4) {
+                    float4 r = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+                    if (a.res) {
+                        float4 e = *reinterpret_cast<const float4*>(a.res + o + c);
+                        r.x += e.x; r.y += e.y; r.z += e.z; r.w += e.w;
+                    }
+                    if (take_src) r = *reinterpret_cast<const float4*>(a.sel_src + o + c);
+                    *reinterpret_cast<float4*>(a.out + o + c) = r;
+                }
+            }
+        }
+    } else if ((t & 31) == 0) {
+        // ===================== MMA issuer: one thread =====================
+        uint32_t it = 0, tile_it = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tile_it) {
+            const uint32_t as = tile_it & 1u, aph = (tile_it >> 1) & 1u;
+            mbar_wait(tempty0 + 8 * as, aph ^ 1u);      // epilogue has drained this accumulator stage
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * 64u;
+            #pragma unroll 1
+            for (int j = 0; j < NCH; ++j, ++it) {
+                const uint32_t stage = it % kTcStages, ph = (it / kTcStages) & 1u;
+                mbar_wait(full0 + 8 * stage, ph);
+                fence_proxy_async();                    // cp.async wrote through the generic proxy; the MMA reads through the async proxy
+                tc_fence_after();
+                const uint32_t sA_hi = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                const uint32_t sA_lo = sA_hi + A_BYTES, sB_hi = sA_lo + A_BYTES, sB_lo = sB_hi + B_BYTES;
+                #pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {        // 4 K steps of 8 tf32 (32 B) inside the 128 B swizzle span
+                    const uint64_t ah = make_desc_sw128(sA_hi + ks * 32), bh = make_desc_sw128(sB_hi + ks * 32);
+                    umma_tf32(tmem_d, ah, bh, IDESC, (j | ks) ? 1u : 0u);
+                    if (PRECISE) {
+                        const uint64_t al = make_desc_sw128(sA_lo + ks * 32), bl = make_desc_sw128(sB_lo + ks * 32);
+                        umma_tf32(tmem_d, al, bh, IDESC, 1u);
+                        umma_tf32(tmem_d, ah, bl, IDESC, 1u);
+                    }
+                }
+                umma_commit(empty0 + 8 * stage);       // stage reusable once these MMAs have read it
+            }
+            umma_commit(tfull0 + 8 * as);               // accumulator complete
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// Optional BatchNorm(eval) + ReLU, then TF32 hi / lo split, once per element (the SIMT kernel re-applies the
+// activation on every gather instead).
+__global__ void __launch_bounds__(256) k_act_split(const float4* __restrict__ in, const float* __restrict__ bn, int c, int bn_off,
+                                                   int bn_stride, int64_t n4, float4* __restrict__ hi, float4* __restrict__ lo) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 x = in[i];
+    if (bn) {
+        const int ch = (int)((i * 4) % c) + bn_off;
+        x.x = fmaxf(fmaf(x.x, bn[ch + 0], bn[bn_stride + ch + 0]), 0.f);
+        x.y = fmaxf(fmaf(x.y, bn[ch + 1], bn[bn_stride + ch + 1]), 0.f);
+        x.z = fmaxf(fmaf(x.z, bn[ch + 2], bn[bn_stride + ch + 2]), 0.f);
+        x.w = fmaxf(fmaf(x.w, bn[ch + 3], bn[bn_stride + ch + 3]), 0.f);
+    }
+    float4 h = make_float4(tf32_rn(x.x), tf32_rn(x.y), tf32_rn(x.z), tf32_rn(x.w));
+    hi[i] = h;
+    if (lo) lo[i] = make_float4(tf32_rn(x.x - h.x), tf32_rn(x.y - h.y), tf32_rn(x.z - h.z), tf32_rn(x.w - h.w));
+}
+
+void act_split(Ctx& cx, const float* in, const float* bn, int c, int bn_off, int bn_stride, int64_t n, float* hi, float* lo) {
+    int64_t n4 = n * c / 4;
+    if (n4 <= 0) return;
+    k_act_split<<<div_up(n4, 256), 256, 0, cx.st>>>((const float4*)in, bn, c, bn_off, bn_stride, n4, (float4*)hi, (float4*)lo);
+    cx.launches++;
+}
+
+// ------------------------------------------------------------------------------------------ host side
+
+// Weight image for the tensor-core kernel: per chunk of 32 K indices a [NP][32] K-major tile, SWIZZLE_128B,
+// TF32 "hi" (low 13 mantissa bits cleared) followed by the "lo" remainder.
+static float host_tf32_rn(float x) {                  // cvt.rna.tf32.f32 on the host (round to nearest, ties away)
+    uint32_t b;
+    std::memcpy(&b, &x, 4);
+    b = (b + 0x1000u) & 0xFFFFE000u;
+    float r;
+    std::memcpy(&r, &b, 4);
+    return r;
+}
+
+std::vector<float> make_tc_weight_image(const float* w_kcico, int kv, int ci, int co) {
+    const int KT = kv * ci, NCH = (KT + 31) / 32, NP = co < 16 ? 16 : co;
+    std::vector<float> img((size_t)NCH * 2 * NP * 32, 0.0f);
+    for (int j = 0; j < NCH; ++j)
+        for (int n = 0; n < NP; ++n)
+            for (int kk = 0; kk < 32; ++kk) {
+                int idx = j * 32 + kk;
+                float val = 0.0f;
+                if (idx < KT && n < co) val = w_kcico[(size_t)idx * co + n];        // [k][ci][co] flattened: idx = k*ci + c
+                float hi = host_tf32_rn(val);
+                float lo = host_tf32_rn(val - hi);
+                int p = kk / 4, e = kk % 4;
+                size_t off = (size_t)n * 32 + (size_t)((p ^ (n & 7)) * 4) + e;
+                img[(size_t)j * 2 * NP * 32 + off] = hi;
+                img[(size_t)j * 2 * NP * 32 + (size_t)NP * 32 + off] = lo;
+            }
+    return img;
+}
+
+template <int CI, int CO, int KV, bool CAT>
+static void launch_tc(Ctx& cx, const TcArgs& a0, bool precise) {
+    TcArgs a = a0;
+    if (a.n_out <= 0) return;
+    a.n_tiles = div_up(a.n_out, 128);
+    constexpr int NP = CO < 16 ? 16 : CO;
+    constexpr size_t smem = (size_t)kTcStages * (2 * 128 * 128 + 2 * NP * 128) + 1024;
+    int grid = std::min(a.n_tiles, kNumSMs);
+    if (precise) {
+        auto kern = k_conv_tc<CI, CO, KV, CAT, true>;
+        SQSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kTcThreads, smem, cx.st>>>(a);
+    } else {
+        auto kern = k_conv_tc<CI, CO, KV, CAT, false>;
+        SQSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kTcThreads, smem, cx.st>>>(a);
+    }
+    cx.launches++;
+}
+
+// Dispatch on the shapes that occur in SmartTreeXX. Returns false for shapes it does not cover.
+bool conv_tc(Ctx& cx, int ci, int co, int kv, bool cat, const float* inA, const float* inB, const float* inA_lo,
+             const float* inB_lo, const int32_t* nbr, const float* wimg, const float* res, const float* sel_src,
+             const uint8_t* sel_flag, float* out, int64_t n_out, bool precise) {
+    TcArgs a;
+    a.inA = inA; a.inB = inB; a.inA_lo = inA_lo; a.inB_lo = inB_lo; a.nbr = nbr; a.wimg = wimg; a.res = res; a.sel_src = sel_src; a.sel_flag = sel_flag;
+    a.out = out; a.n_out = (int)n_out; a.n_tiles = 0;
+#define SQSM_TC_CASE(CI_, CO_, KV_, CAT_)                                         \
+    if (ci == CI_ && co == CO_ && kv == KV_ && cat == CAT_) {                     \
+        launch_tc<CI_, CO_, KV_, CAT_>(cx, a, precise);                           \
+        return true;                                                              \
+    }
+    SQSM_TC_CASE(16, 16, 27, false) SQSM_TC_CASE(32, 32, 27, false) SQSM_TC_CASE(64, 64, 27, false)
+    SQSM_TC_CASE(32, 16, 27, true) SQSM_TC_CASE(64, 32, 27, true)
+    SQSM_TC_CASE(32, 16, 1, true) SQSM_TC_CASE(64, 32, 1, true)
+    SQSM_TC_CASE(8, 16, 8, false) SQSM_TC_CASE(16, 32, 8, false) SQSM_TC_CASE(32, 64, 8, false)
+    SQSM_TC_CASE(32, 16, 8, false) SQSM_TC_CASE(64, 32, 8, false)
+#undef SQSM_TC_CASE
+    return false;
+}
+
+}  // namespace sqsm

@@ -5,6 +5,7 @@
 // the thunks of get_pipeline(); nothing crosses PCIe per batch (the reference copies every batch
 // back with .cpu().numpy(), :107-108).
 #include "engine.h"
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -35,14 +36,15 @@ struct sqsm_engine {
     bool early_stopped = false;
     bool capture = false;
     DebugCapture dbg;
-    bool prof_on = false;
-    std::map<std::string, ConvProfile> prof;
+    std::map<std::string, ConvProfile> prof;   // resolved kernel-family records
+    cudaEvent_t tm_a = nullptr, tm_b = nullptr; // sqsm_timer_start / stop
     SkeletalResult sk;
     bool sk_valid = false;
     DBuf<int64_t> edges;            // cached radius graph of `sk`
     int64_t n_edges = 0;
     double edges_r = -1.0;
     int64_t max_entries_per_pass = 48ll << 20;
+    size_t pool_reserved = 0;
 };
 
 static std::string g_create_error;
@@ -122,7 +124,31 @@ extern "C" int sqsm_set_weight(sqsm_handle h, const char* name, const float* dat
 extern "C" int sqsm_finalize_weights(sqsm_handle h) {
     SQSM_API_BEGIN(h)
     net_upload(h->cx, h->nw, h->state, h->cfg.down_kernel_flip != 0);
+    int mode = h->cfg.conv_mode;
+    if (mode == 0) { const char* env = getenv("SQSM_CONV_MODE"); mode = env ? atoi(env) : 2; }
+    SQSM_CHECK(mode >= 1 && mode <= 3, "conv_mode must be 0..3");
+    h->nw.mode = mode - 1;                                   // 0 FFMA, 1 3xTF32, 2 TF32
+    if (const char* env = getenv("SQSM_TC_MIN_CO")) h->nw.tc_min_co = atoi(env);
     SQSM_API_END(h)
+}
+
+// Pre-grow the stream-ordered memory pool so that the temporaries of a step are carved out of memory the
+// pool already owns (growing the pool mid-step costs milliseconds per allocation).
+static void reserve_pool(sqsm_engine* h, int64_t n_points) {
+    size_t want = (size_t)n_points * 2200 + (1ull << 30);        // ~1.5-2 kB of tables and features per point
+    if (want <= h->pool_reserved) return;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return;
+    want = std::min(want, (size_t)(free_b * 0.8));
+    if (want <= h->pool_reserved) return;
+    void* p = nullptr;
+    if (cudaMallocAsync(&p, want, h->cx.st) == cudaSuccess) {
+        cudaFreeAsync(p, h->cx.st);
+        cudaStreamSynchronize(h->cx.st);
+        h->pool_reserved = want;
+    } else {
+        cudaGetLastError();
+    }
 }
 
 static void reset_state(sqsm_engine* h) {
@@ -153,6 +179,7 @@ extern "C" int sqsm_set_points_f64(sqsm_handle h, const double* xyz, int64_t n) 
     h->n = n;
     reset_state(h);
     SQSM_CUDA(cudaStreamSynchronize(st));
+    reserve_pool(h, n);
     SQSM_API_END(h)
 }
 
@@ -167,6 +194,7 @@ extern "C" int sqsm_set_points_dev_f32(sqsm_handle h, const float* d_xyz, int64_
     h->n = n;
     reset_state(h);
     SQSM_CUDA(cudaStreamSynchronize(st));
+    reserve_pool(h, n);
     SQSM_API_END(h)
 }
 
@@ -220,7 +248,11 @@ extern "C" int sqsm_contract_step(sqsm_handle h, SqsmIterStats* stats) {
     StageTimer T0(st);
     T0.mark();
     TilingResult tl;
-    tile_points(cx, h->P.p, h->n, cfg.cube_size, cfg.buffer_size, cfg.voxel_size, cfg.batch_size, tl);   // :85-91
+    {
+        Trace tr(cx, "tile_points");
+        ProfScope ps(cx, "tiling", (double)h->n * 12.0 * 3 + 0.0, 0.0);
+        tile_points(cx, h->P.p, h->n, cfg.cube_size, cfg.buffer_size, cfg.voxel_size, cfg.batch_size, tl);   // :85-91
+    }
     T0.mark();
     s.n_entries = tl.n_entries;
     s.n_cubes = tl.n_samples;
@@ -245,18 +277,30 @@ extern "C" int sqsm_contract_step(sqsm_handle h, SqsmIterStats* stats) {
         Level0Rows rows;
         DBuf<int32_t> ent_row;
         int64_t n_out = 0;
-        build_level0(cx, h->P.p, h->D.p, tl, s0, s1, cfg.batch_size, cfg.voxel_size, lv[0], rows, out_base, &n_out, ent_row);
+        {
+            // B_vox of SURVEY 8(d): per entry 24 B in (point + displacement), 8 B key, 16 B coordinates, 12 B features
+            Trace tr(cx, "build_level0");
+            ProfScope ps(cx, "voxelise", (double)(tl.start[s1] - tl.start[s0]) * (24.0 + 8.0 + 16.0 + 12.0), 0.0);
+            build_level0(cx, h->P.p, h->D.p, tl, s0, s1, cfg.batch_size, cfg.voxel_size, lv[0], rows, out_base, &n_out, ent_row);
+        }
         ent_row.release();
+        ProfScope* rs = new ProfScope(cx, "rulebook", 0.0, 0.0);
         T.mark();
         int64_t far = 0;
-        build_subm(cx, lv[0], batch0, nb, cfg.batch_size, &far);
+        { Trace tr(cx, "build_subm L0"); build_subm(cx, lv[0], batch0, nb, cfg.batch_size, &far); }
         s.far_face_rows += far;
         int n_levels = 1;
         for (int l = 0; l + 1 < kLevels; ++l) {
-            if (!build_down(cx, lv[l], lv[l + 1], batch0, nb, cfg.batch_size)) break;
-            build_subm(cx, lv[l + 1], batch0, nb, cfg.batch_size, nullptr);
+            { Trace tr(cx, "build_down"); if (!build_down(cx, lv[l], lv[l + 1], batch0, nb, cfg.batch_size)) break; }
+            { Trace tr(cx, "build_subm"); build_subm(cx, lv[l + 1], batch0, nb, cfg.batch_size, nullptr); }
             n_levels = l + 2;
         }
+        {   // algorithmic bytes of the rulebook stage: 27 int32 table entries written per row + brick lines read
+            double by = 0;
+            for (int l = 0; l < n_levels; ++l) by += (double)lv[l].n * (27.0 * 4 + 6.0) + (double)lv[l].map.n_bricks * 128.0 * 2;
+            rs->r.bytes = by;
+        }
+        delete rs;
         T.mark();
         s.n_vox += lv[0].n;
         s.pairs_l0 += lv[0].pairs;
@@ -264,7 +308,7 @@ extern "C" int sqsm_contract_step(sqsm_handle h, SqsmIterStats* stats) {
         if (n_levels > 2) { s.n_rows_l2 += lv[2].n; s.pairs_l2 += lv[2].pairs; }
         if (n_levels > 3) { s.n_rows_l3 += lv[3].n; s.pairs_l3 += lv[3].pairs; }
         ForwardBuffers fb;
-        net_forward(cx, h->nw, lv, rows, n_levels, fb, h->capture, newP.p, newD.p, h->prof_on ? &h->prof : nullptr);  // :100-108
+        { Trace tr(cx, "net_forward"); net_forward(cx, h->nw, lv, rows, n_levels, fb, h->capture, newP.p, newD.p); }  // :100-108
         T.mark();
         SQSM_CUDA(cudaStreamSynchronize(st));
         ms_vox += T.between(0, 1);
@@ -286,12 +330,19 @@ extern "C" int sqsm_contract_step(sqsm_handle h, SqsmIterStats* stats) {
         s0 = s1;
     }
     s.n_out = out_base;
+    if (Trace::enabled()) fprintf(stderr, "[trace] ---- end of passes, n_out %lld\n", (long long)out_base);
     SQSM_CHECK(out_base > 0, "contraction produced no interior voxel");
     bool accept = true;
     if (cfg.monitored_by_chamfer_distance) {                                 // :112-128
         StageTimer T(st);
         T.mark();
-        double cd = chamfer_distance(cx, h->P.p, h->n, newP.p, out_base, (double)cfg.voxel_size);
+        double cd;
+        {
+            // B_cd of SURVEY 8(d): both clouds read (12 B/point) + voxel means written and read (2 x 24 B/voxel ~ per point)
+            Trace tr(cx, "chamfer");
+            ProfScope ps(cx, "chamfer", (double)(h->n + out_base) * (12.0 + 2 * 20.0), 0.0);
+            cd = chamfer_distance(cx, h->P.p, h->n, newP.p, out_base, (double)cfg.voxel_size);
+        }
         T.mark();
         SQSM_CUDA(cudaStreamSynchronize(st));
         ms_cd = T.between(0, 1);
@@ -340,6 +391,7 @@ extern "C" int sqsm_skeletal_sample(sqsm_handle h, double voxel, int64_t* m, int
     SQSM_CHECK(h->n > 0 && m, "no state");
     cudaStream_t st = h->cx.st;
     if (!h->sk_valid) {
+        ProfScope ps(h->cx, "skeletal", (double)h->n * (24.0 + 4.0), 0.0);
         skeletal_sample(h->cx, h->P.p, h->D.p, h->n, voxel, h->sk);
         h->sk_valid = true;
         h->edges_r = -1.0;
@@ -369,6 +421,7 @@ extern "C" int sqsm_radius_graph(sqsm_handle h, double r, int64_t* n_edges, int6
     SQSM_API_BEGIN(h)
     SQSM_CHECK(h->sk_valid && n_edges, "call sqsm_skeletal_sample first");
     if (h->edges_r != r) {                                   // computed once per skeletal sample and radius
+        ProfScope ps(h->cx, "radius_graph", (double)h->sk.m * 12.0, 0.0);
         radius_graph(h->cx, h->sk.pts.p, h->sk.m, r, h->edges, &h->n_edges);
         h->edges_r = r;
     }
@@ -524,26 +577,80 @@ extern "C" int sqsm_debug_features(sqsm_handle h, const char* stage, int32_t* le
 
 // ---------------------------------------------------------------------------------- measurement hooks
 
+static void resolve_profile(sqsm_engine* h) {
+    Ctx& cx = h->cx;
+    if (cx.pending.empty()) return;
+    SQSM_CUDA(cudaStreamSynchronize(cx.st));
+    for (auto& r : cx.pending) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        ConvProfile& c = h->prof[cx.fam_names[r.fam]];
+        c.ms += ms; c.launches += r.launches; c.bytes += r.bytes; c.flops += r.flops;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    cx.pending.clear();
+}
+
 extern "C" int sqsm_profile_enable(sqsm_handle h, int32_t enable) {
     SQSM_API_BEGIN(h)
-    h->prof_on = enable != 0;
+    h->cx.prof_on = enable != 0;
     SQSM_API_END(h)
 }
 
 extern "C" int sqsm_profile_reset(sqsm_handle h) {
     SQSM_API_BEGIN(h)
+    resolve_profile(h);
     h->prof.clear();
     SQSM_API_END(h)
 }
 
-extern "C" int sqsm_profile_get(sqsm_handle h, const char* family, double* ms, int64_t* launches, double* bytes) {
+extern "C" int sqsm_profile_get(sqsm_handle h, const char* family, double* ms, int64_t* launches, double* bytes,
+                                double* flops) {
     SQSM_API_BEGIN(h)
     SQSM_CHECK(family, "null family");
+    resolve_profile(h);
     ConvProfile p;
     auto it = h->prof.find(family);
     if (it != h->prof.end()) p = it->second;
     if (ms) *ms = p.ms;
     if (launches) *launches = p.launches;
     if (bytes) *bytes = p.bytes;
+    if (flops) *flops = p.flops;
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_profile_families(sqsm_handle h, char* buf, int64_t capacity) {
+    SQSM_API_BEGIN(h)
+    resolve_profile(h);
+    std::string all;
+    for (auto& kv : h->prof) { if (!all.empty()) all += ","; all += kv.first; }
+    SQSM_CHECK(buf && capacity > (int64_t)all.size(), "buffer too small");
+    std::memcpy(buf, all.c_str(), all.size() + 1);
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_timer_start(sqsm_handle h) {
+    SQSM_API_BEGIN(h)
+    if (!h->tm_a) { SQSM_CUDA(cudaEventCreate(&h->tm_a)); SQSM_CUDA(cudaEventCreate(&h->tm_b)); }
+    SQSM_CUDA(cudaStreamSynchronize(h->cx.st));
+    SQSM_CUDA(cudaEventRecord(h->tm_a, h->cx.st));
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_timer_stop(sqsm_handle h, double* ms) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(h->tm_a && ms, "timer not started");
+    SQSM_CUDA(cudaEventRecord(h->tm_b, h->cx.st));
+    SQSM_CUDA(cudaEventSynchronize(h->tm_b));
+    float f = 0;
+    SQSM_CUDA(cudaEventElapsedTime(&f, h->tm_a, h->tm_b));
+    *ms = f;
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_launch_count(sqsm_handle h, int64_t* n) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(n, "null argument");
+    *n = h->cx.launches;
     SQSM_API_END(h)
 }

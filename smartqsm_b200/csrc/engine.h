@@ -54,6 +54,7 @@ struct ConvW {                          // one convolution, device resident
     int ci = 0, co = 0, kv = 0;
     float* w = nullptr;                 // [kv][ci][co]
     float* bn = nullptr;                // [2][ci] alpha, beta of the BatchNorm+ReLU in FRONT of the conv (or null)
+    float* wimg = nullptr;              // tensor-core weight image (conv_tc.cu) or null
 };
 
 struct HeadW {                          // output_layer BN + both MLP heads; index 0 = offset, 1 = regression
@@ -68,6 +69,8 @@ struct NetWeights {
     DBuf<float> blob;
     HeadW head;
     bool ready = false;
+    int mode = 1;                       // 0 = fp32 FFMA everywhere, 1 = tcgen05 3xTF32 (fp32-class), 2 = tcgen05 single-pass TF32
+    int tc_min_co = 16;                 // layers with at least this many output channels use the tensor-core kernel
 };
 
 struct Net;                             // conv.cu
@@ -82,8 +85,7 @@ struct ForwardBuffers {
 };
 struct ConvProfile { double ms = 0; int64_t launches = 0; double bytes = 0; double flops = 0; };
 void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Rows& rows, int n_levels,
-                 ForwardBuffers& fb, bool keep, float* d_newP, float* d_newD,
-                 std::map<std::string, ConvProfile>* prof);
+                 ForwardBuffers& fb, bool keep, float* d_newP, float* d_newD);
 
 // structure.cu
 struct TilingResult {

@@ -151,101 +151,123 @@ __global__ void __launch_bounds__(256) k_voxel_mean(double* __restrict__ sum, co
     sum[3 * r + 2] = __ddiv_rn(sum[3 * r + 2], c);
 }
 
-// One block per query brick of map A; candidates are the voxel means of map B in the 27 bricks around
-// it, staged brick by brick through shared memory.  A query whose best distance exceeds the lower
-// bound of the searched 3x3x3 block continues with growing rings of bricks (exact 1-NN).
-constexpr int kNNThreads = 128;
-__global__ void __launch_bounds__(kNNThreads) k_nn_sqdist(const Brick* __restrict__ A, int nA, const double* __restrict__ meanA,
-                                                          BrickHash hB, const Brick* __restrict__ B, const double* __restrict__ meanB,
-                                                          double brick_edge, int max_ring, double* __restrict__ acc) {
-    __shared__ double cand[512 * 3];
-    __shared__ int s_nb[27];
-    __shared__ double s_red[kNNThreads / 32];
-    const int t = threadIdx.x;
-    double local_sum = 0.0;
-    for (int a = blockIdx.x; a < nA; a += gridDim.x) {
-        const Brick& qa = A[a];
-        const uint64_t key = qa.key;
-        const int bz = (int)key_z(key), by = (int)key_y(key), bx = (int)key_x(key);
-        __syncthreads();
-        if (t < 27) {
-            int z = bz + t / 9 - 1, y = by + (t / 3) % 3 - 1, x = bx + t % 3 - 1;
-            int id = -1;
-            if (z >= 0 && y >= 0 && x >= 0 && z < 65536 && y < 65536 && x < 65536)
-                id = hash_find(hB, pack_key(0u, (uint32_t)z, (uint32_t)y, (uint32_t)x));
-            s_nb[t] = id;
-        }
-        __syncthreads();
-        const int nq = qa.count;
-        constexpr int QPT = 512 / kNNThreads;
-        double q[QPT][3], best[QPT];
-        #pragma unroll
-        for (int j = 0; j < QPT; ++j) {
-            int qi = t + j * kNNThreads;
-            best[j] = 1e300;
-            if (qi < nq) {
-                q[j][0] = meanA[3 * (size_t)(qa.base + qi) + 0];
-                q[j][1] = meanA[3 * (size_t)(qa.base + qi) + 1];
-                q[j][2] = meanA[3 * (size_t)(qa.base + qi) + 2];
-            } else { q[j][0] = q[j][1] = q[j][2] = 0.0; }
-        }
-        for (int nb = 0; nb < 27; ++nb) {
-            int id = s_nb[nb];
-            if (id < 0) continue;                                   // block-uniform
-            const int cbase = B[id].base, cn = B[id].count;
-            __syncthreads();
-            for (int i = t; i < cn * 3; i += kNNThreads) cand[i] = meanB[3 * (size_t)cbase + i];
-            __syncthreads();
-            #pragma unroll
-            for (int j = 0; j < QPT; ++j) {
-                if (t + j * kNNThreads >= nq) continue;
-                double bj = best[j];
-                for (int c = 0; c < cn; ++c) {
-                    double dx = q[j][0] - cand[3 * c], dy = q[j][1] - cand[3 * c + 1], dz = q[j][2] - cand[3 * c + 2];
-                    double d2 = dx * dx + dy * dy + dz * dz;
-                    bj = fmin(bj, d2);
-                }
-                best[j] = bj;
-            }
-        }
-        // exactness: the query lies inside brick b; once every brick within Chebyshev distance R of b has
-        // been searched, any other point is at least R * brick_edge away.  R = 1 after the 27-neighbourhood.
-        #pragma unroll
-        for (int j = 0; j < QPT; ++j) {
-            if (t + j * kNNThreads >= nq) continue;
-            int ring = 1;
-            double bj = best[j];
-            while (bj > (double)ring * brick_edge * (double)ring * brick_edge && ring < max_ring) {
-                ++ring;
-                for (int dz = -ring; dz <= ring; ++dz)
-                    for (int dy = -ring; dy <= ring; ++dy)
-                        for (int dx = -ring; dx <= ring; ++dx) {
-                            if (max(max(abs(dz), abs(dy)), abs(dx)) != ring) continue;
-                            int z = bz + dz, y = by + dy, x = bx + dx;
-                            if (z < 0 || y < 0 || x < 0 || z > 65535 || y > 65535 || x > 65535) continue;
-                            int id = hash_find(hB, pack_key(0u, (uint32_t)z, (uint32_t)y, (uint32_t)x));
-                            if (id < 0) continue;
-                            const int cbase = B[id].base, cn = B[id].count;
-                            for (int c = 0; c < cn; ++c) {
-                                double ddx = q[j][0] - meanB[3 * (size_t)(cbase + c)], ddy = q[j][1] - meanB[3 * (size_t)(cbase + c) + 1],
-                                       ddz = q[j][2] - meanB[3 * (size_t)(cbase + c) + 2];
-                                bj = fmin(bj, ddx * ddx + ddy * ddy + ddz * ddz);
-                            }
-                        }
-            }
-            local_sum += bj;
+// For every brick of map A: (first row, count) of the 27 bricks of map B around the same coordinates.
+__global__ void __launch_bounds__(256) k_cross_neighbours(const Brick* __restrict__ A, int nA, BrickHash hB,
+                                                          const Brick* __restrict__ B, int2* __restrict__ abn) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int a = t >> 5, j = t & 31;
+    if (a >= nA) return;
+    int2 r = make_int2(0, 0);
+    if (j < 27) {
+        uint64_t key = A[a].key;
+        int z = (int)key_z(key) + j / 9 - 1, y = (int)key_y(key) + (j / 3) % 3 - 1, x = (int)key_x(key) + j % 3 - 1;
+        if (z >= 0 && y >= 0 && x >= 0 && z < 65536 && y < 65536 && x < 65536) {
+            int id = hash_find(hB, pack_key(0u, (uint32_t)z, (uint32_t)y, (uint32_t)x));
+            if (id >= 0) r = make_int2(B[id].base, B[id].count);
         }
     }
-    // block reduction of the squared distances
+    abn[(size_t)a * 32 + j] = r;
+}
+
+// Exact 1-NN squared distances from the voxel means of map A to those of map B, summed.
+// One warp per query brick.  Lanes are (query, candidate slice) pairs: a brick with nq <= 16 queries
+// gives every query S = 32 / pow2(nq) lanes that scan interleaved slices of the candidates.  Bricks of B
+// are visited centre first; a brick is skipped when, for every query of the warp, its nearest possible
+// point is not closer than the best distance found so far.  The query lies inside its brick, so after
+// the 27-neighbourhood everything else is at least one brick edge away; a query whose best distance
+// exceeds that bound keeps growing rings of bricks (hash probes) until it does not - exact 1-NN like the
+// KD-tree search of Open3D's compute_point_cloud_distance.
+constexpr int kNNThreads = 256;
+__global__ void __launch_bounds__(kNNThreads) k_nn_sqdist(const Brick* __restrict__ A, int nA, const double* __restrict__ meanA,
+                                                          const int2* __restrict__ abn, BrickHash hB,
+                                                          const Brick* __restrict__ B, const double* __restrict__ meanB,
+                                                          const __grid_constant__ GridParams g, int max_ring,
+                                                          double* __restrict__ acc, unsigned long long* __restrict__ n_fallback) {
+    __shared__ double s_red[kNNThreads / 32];
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * kNNThreads + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * kNNThreads) >> 5;
+    const double edge = 8.0 * g.voxel;
+    const double slack = 1e-6 * edge;                      // voxel means may sit an ulp outside their voxel
+    double local_sum = 0.0;
+    unsigned fb = 0;
+    for (int a = warp; a < nA; a += n_warps) {
+        const int nq = A[a].count, qbase = A[a].base;
+        const uint64_t key = A[a].key;
+        const int2 mine = abn[(size_t)a * 32 + lane];
+        const int bz = (int)key_z(key), by = (int)key_y(key), bx = (int)key_x(key);
+        int S = 1;                                          // lanes per query
+        if (nq <= 16) { int p2 = 1; while (p2 < nq) p2 <<= 1; S = 32 / p2; }
+        const int sl = lane % S;
+        for (int q0 = 0; q0 < nq; q0 += 32 / S) {
+            const int qi = q0 + lane / S;
+            const bool valid = qi < nq;
+            double qx = 0, qy = 0, qz = 0;
+            if (valid) {
+                qx = meanA[3 * (size_t)(qbase + qi)];
+                qy = meanA[3 * (size_t)(qbase + qi) + 1];
+                qz = meanA[3 * (size_t)(qbase + qi) + 2];
+            }
+            // offset of the query inside its brick (x, y, z)
+            const double lx = qx - (g.mn[0] + (double)bx * edge), ly = qy - (g.mn[1] + (double)by * edge),
+                         lz = qz - (g.mn[2] + (double)bz * edge);
+            double best = 1e300;
+            #pragma unroll 1
+            for (int step = 0; step < 27; ++step) {
+                const int nb = (step == 0) ? 13 : (step <= 13 ? step - 1 : step);      // centre brick first
+                const int2 rc = make_int2(__shfl_sync(0xFFFFFFFFu, mine.x, nb), __shfl_sync(0xFFFFFFFFu, mine.y, nb));
+                if (rc.y == 0) continue;                                             // warp-uniform
+                const int dz = nb / 9 - 1, dy = (nb / 3) % 3 - 1, dx = nb % 3 - 1;
+                double gx = dx == 0 ? 0.0 : (dx < 0 ? lx : edge - lx), gy = dy == 0 ? 0.0 : (dy < 0 ? ly : edge - ly),
+                       gz = dz == 0 ? 0.0 : (dz < 0 ? lz : edge - lz);
+                gx = fmax(gx - slack, 0.0); gy = fmax(gy - slack, 0.0); gz = fmax(gz - slack, 0.0);
+                const double lb2 = gx * gx + gy * gy + gz * gz;
+                if (__all_sync(0xFFFFFFFFu, !valid || best <= lb2)) continue;
+                const double* c = meanB + 3 * (size_t)rc.x;
+                double bl = best;
+                for (int i = sl; i < rc.y; i += S) {
+                    double ex = qx - c[3 * i], ey = qy - c[3 * i + 1], ez = qz - c[3 * i + 2];
+                    bl = fmin(bl, ex * ex + ey * ey + ez * ez);
+                }
+                for (int d = 1; d < S; d <<= 1) bl = fmin(bl, __shfl_xor_sync(0xFFFFFFFFu, bl, d));
+                best = bl;
+            }
+            if (valid && sl == 0) {
+                int ring = 1;
+                if (best > edge * edge) ++fb;
+                while (best > (double)ring * edge * (double)ring * edge && ring < max_ring) {
+                    ++ring;
+                    for (int dz = -ring; dz <= ring; ++dz)
+                        for (int dy = -ring; dy <= ring; ++dy) {
+                            const bool shell = (abs(dz) == ring) || (abs(dy) == ring);
+                            for (int dx = -ring; dx <= ring; dx += (shell ? 1 : 2 * ring)) {
+                                int z = bz + dz, y = by + dy, x = bx + dx;
+                                if (z < 0 || y < 0 || x < 0 || z > 65535 || y > 65535 || x > 65535) continue;
+                                int id = hash_find(hB, pack_key(0u, (uint32_t)z, (uint32_t)y, (uint32_t)x));
+                                if (id < 0) continue;
+                                const int cb = B[id].base, cn = B[id].count;
+                                for (int i = 0; i < cn; ++i) {
+                                    double ex = qx - meanB[3 * (size_t)(cb + i)], ey = qy - meanB[3 * (size_t)(cb + i) + 1],
+                                           ez = qz - meanB[3 * (size_t)(cb + i) + 2];
+                                    best = fmin(best, ex * ex + ey * ey + ez * ez);
+                                }
+                            }
+                        }
+                }
+                local_sum += best;
+            }
+        }
+    }
     #pragma unroll
     for (int d = 16; d > 0; d >>= 1) local_sum += __shfl_xor_sync(0xFFFFFFFFu, local_sum, d);
+    fb = __reduce_add_sync(0xFFFFFFFFu, fb);
+    if (lane == 0) s_red[threadIdx.x >> 5] = local_sum;
+    if (lane == 0 && fb) atomicAdd(n_fallback, (unsigned long long)fb);
     __syncthreads();
-    if ((t & 31) == 0) s_red[t >> 5] = local_sum;
-    __syncthreads();
-    if (t == 0) {
-        double s = 0.0;
-        for (int w = 0; w < kNNThreads / 32; ++w) s += s_red[w];
-        atomicAdd(acc, s);
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kNNThreads / 32; ++w) t += s_red[w];
+        atomicAdd(acc, t);
     }
 }
 
@@ -256,7 +278,8 @@ struct VoxelMeans {
 
 static void voxel_means(Ctx& cx, const float* d_P, int64_t n, const double mn[3], double voxel, VoxelMeans& vm) {
     cudaStream_t st = cx.st;
-    grid_build(cx, d_P, n, mn, voxel, vm.gm);
+    { Trace tr(cx, " cd grid_build"); grid_build(cx, d_P, n, mn, voxel, vm.gm); }
+    Trace tr2(cx, " cd accumulate");
     int64_t rows = vm.gm.map.n_rows;
     vm.mean.alloc(rows * 3, st);
     vm.mean.zero();
@@ -275,20 +298,38 @@ double chamfer_distance(Ctx& cx, const float* d_P, int64_t np, const float* d_Q,
     cloud_bounds(cx, d_Q, nq, mnQ, mxQ);
     for (int a = 0; a < 3; ++a) { mn[a] = std::min(mnP[a], mnQ[a]); mx[a] = std::max(mxP[a], mxQ[a]); }   // :116-117
     VoxelMeans A, B;
-    voxel_means(cx, d_P, np, mn, voxel, A);                                                                // :120
-    voxel_means(cx, d_Q, nq, mn, voxel, B);                                                                // :121
+    {
+        ProfScope ps(cx, "cd_voxel_means", (double)(np + nq) * (12.0 + 2 * 20.0), 0.0);
+        voxel_means(cx, d_P, np, mn, voxel, A);                                                            // :120
+        voxel_means(cx, d_Q, nq, mn, voxel, B);                                                            // :121
+    }
+    Trace trnn(cx, " cd nn");
+    ProfScope ps_nn(cx, "cd_nn", (double)(A.gm.map.n_rows + B.gm.map.n_rows) * 24.0 * 2, 0.0);
     double ext = 0;
     for (int a = 0; a < 3; ++a) ext = std::max(ext, mx[a] - mn[a]);
     const double edge = 8.0 * voxel;
     int max_ring = (int)std::ceil(ext / edge) + 2;
     DBuf<double> acc(2, st);
+    DBuf<unsigned long long> nfb(2, st);
     acc.zero();
-    int gA = std::min(A.gm.map.n_bricks, kNumSMs * 16), gB = std::min(B.gm.map.n_bricks, kNumSMs * 16);
-    k_nn_sqdist<<<gA, kNNThreads, 0, st>>>(A.gm.map.bricks.p, A.gm.map.n_bricks, A.mean.p, B.gm.map.view(),
-                                           B.gm.map.bricks.p, B.mean.p, edge, max_ring, acc.p);
-    k_nn_sqdist<<<gB, kNNThreads, 0, st>>>(B.gm.map.bricks.p, B.gm.map.n_bricks, B.mean.p, A.gm.map.view(),
-                                           A.gm.map.bricks.p, A.mean.p, edge, max_ring, acc.p + 1);
-    cx.launches += 2;
+    nfb.zero();
+    const int nA = A.gm.map.n_bricks, nB = B.gm.map.n_bricks;
+    DBuf<int2> abn((int64_t)nA * 32, st), ban((int64_t)nB * 32, st);
+    k_cross_neighbours<<<div_up((int64_t)nA * 32, 256), 256, 0, st>>>(A.gm.map.bricks.p, nA, B.gm.map.view(),
+                                                                      B.gm.map.bricks.p, abn.p);
+    k_cross_neighbours<<<div_up((int64_t)nB * 32, 256), 256, 0, st>>>(B.gm.map.bricks.p, nB, A.gm.map.view(),
+                                                                      A.gm.map.bricks.p, ban.p);
+    int gA = std::min(div_up(nA, kNNThreads / 32), kNumSMs * 8), gB = std::min(div_up(nB, kNNThreads / 32), kNumSMs * 8);
+    k_nn_sqdist<<<gA, kNNThreads, 0, st>>>(A.gm.map.bricks.p, nA, A.mean.p, abn.p, B.gm.map.view(), B.gm.map.bricks.p,
+                                           B.mean.p, A.gm.g, max_ring, acc.p, nfb.p);
+    k_nn_sqdist<<<gB, kNNThreads, 0, st>>>(B.gm.map.bricks.p, nB, B.mean.p, ban.p, A.gm.map.view(), A.gm.map.bricks.p,
+                                           A.mean.p, A.gm.g, max_ring, acc.p + 1, nfb.p + 1);
+    cx.launches += 4;
+    if (Trace::enabled()) {
+        auto f = nfb.to_host();
+        fprintf(stderr, "[trace]  cd nn: ring-search fallbacks %llu of %lld, %llu of %lld\n", f[0], (long long)A.gm.map.n_rows,
+                f[1], (long long)B.gm.map.n_rows);
+    }
     double h[2];
     SQSM_CUDA(cudaMemcpyAsync(h, acc.p, sizeof(h), cudaMemcpyDeviceToHost, st));
     SQSM_CUDA(cudaStreamSynchronize(st));

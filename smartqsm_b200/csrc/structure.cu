@@ -372,7 +372,10 @@ void build_level0(Ctx& cx, const float* d_P, const float* d_D, const TilingResul
     k_entry_voxel<<<grid, 256, 0, st>>>(d_P, tl.ent_sample.p, tl.ent_val.p, e0, n, tl.d_samples.p, voxel_size,
                                         ent_key.p, ent_pos.p);
     cx.launches++;
-    brickmap_build(cx, L0.map, ent_key.p, ent_pos.p, n, ent_brick.p);
+    {
+        ProfScope ps(cx, "vx_brickmap", (double)n * 14.0 * 2, 0.0);
+        brickmap_build(cx, L0.map, ent_key.p, ent_pos.p, n, ent_brick.p);
+    }
     L0.n = L0.map.n_rows;
     SQSM_CHECK(L0.n > 0, "no voxel survived voxelisation");
     int64_t n0 = L0.n;
@@ -472,6 +475,7 @@ void build_subm(Ctx& cx, LevelTables& L, int batch0, int n_batches, int batch_si
     if (L.n == 0) return;
     brickmap_build_neighbours(cx, L.map);
     L.nbr.alloc(27 * L.n, st);
+    ProfScope ps(cx, "rb_subm_nbr", (double)L.n * (27.0 * 4 + 6.0), 0.0);
     DBuf<unsigned long long> stats(2, st);
     stats.zero();
     k_subm_nbr<<<div_up(L.n, 256), 256, 0, st>>>(L.map.bricks.p, L.map.bnbr.p, L.row_brick.p, L.row_pos.p, L.n,
@@ -573,7 +577,10 @@ bool build_down(Ctx& cx, LevelTables& L, LevelTables& Ln, int batch0, int n_batc
     k_row_desc<<<div_up(n, 256), 256, 0, st>>>(L.map.bricks.p, L.row_brick.p, n, L.desc.p, batch_size, batch0,
                                                L.row_desc.p);
     cx.launches++;
-    brickmap_build(cx, Ln.map, ent_key.p, ent_pos.p, n, ent_brick.p);
+    {
+        ProfScope ps(cx, "rb_brickmap", (double)n * 14.0 * 2, 0.0);
+        brickmap_build(cx, Ln.map, ent_key.p, ent_pos.p, n, ent_brick.p);
+    }
     Ln.n = Ln.map.n_rows;
     L.parent.alloc(n, st);
     L.inv.alloc(8 * n, st);

@@ -15,9 +15,13 @@ from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
 
-ACT_TOL = 2e-5        # activations: max |gpu - oracle| / max |oracle| per tensor (fp32 FFMA, different summation order)
-POS_TOL = 4e-6        # contracted positions: absolute, metres, per coordinate of ~10 m magnitude (few ulps + pred error)
-DISP_TOL = 2e-5       # displacements: relative to max |displacement|
+# Tolerances per arithmetic mode (measured by scripts/precision_report.py; see DESIGN.md "Numerics"):
+#   ffma  fp32 FFMA everywhere: activations ~5e-7 of the tensor scale, the fp32-vs-fp64 oracle gap is 2e-7
+#   tc3   tcgen05 3xTF32 for the 16-64 channel layers: ~1.5e-5 at the deepest level (the tensor core's fp32
+#         accumulation chain, not the operand split, sets this floor)
+ACT_TOL = {1: 5e-6, 2: 4e-5, 0: 4e-5}      # activations: max |gpu - oracle| / max |oracle| per tensor
+DISP_TOL = {1: 1e-5, 2: 6e-5, 0: 6e-5}     # displacements: relative to max |displacement|
+POS_TOL = {1: 2e-6, 2: 1e-5, 0: 1e-5}      # contracted positions: absolute metres on coordinates of ~10 m
 
 
 def make_engine(state, **kw):
@@ -38,12 +42,16 @@ def run_gpu_iteration(state, pts64, batch_size=16, disp=None, **kw):
     return eng, st
 
 
-def check_iteration(state, pts64, batch_size=16, disp=None, check_float=True):
+MODES = {"ffma": 1, "tc3": 2}      # fp32 FFMA everywhere / tcgen05 3xTF32 for the 16-64 channel layers (default)
+
+
+def check_iteration(state, pts64, batch_size=16, disp=None, check_float=True, conv_mode=0):
+    act_tol = ACT_TOL[conv_mode if conv_mode in ACT_TOL else 0]
     p32 = pts64.astype(np.float32)
     d32 = np.zeros_like(p32) if disp is None else disp.astype(np.float32)
     w = ON.Weights(state)
     Po, Do, tr = OC.contract_once(p32, d32, w, batch_size=batch_size, keep=True)
-    eng, st = run_gpu_iteration(state, pts64, batch_size, disp)
+    eng, st = run_gpu_iteration(state, pts64, batch_size, disp, conv_mode=conv_mode)
 
     # ---- level-0 voxels in canonical order: coordinates, winners, interior mask (bit-exact)
     o_idx = np.concatenate([np.concatenate([np.full((len(v.coords_zyx), 1), si, np.int32), v.coords_zyx], axis=1)
@@ -100,26 +108,33 @@ def check_iteration(state, pts64, batch_size=16, disp=None, check_float=True):
                 continue
         assert g.shape == o.shape, (name, g.shape, o.shape)
         err = H.rel_err(g, o[g2o[lvl]])
-        assert err <= ACT_TOL, f"{name}: relative error {err:.3e} > {ACT_TOL}"
+        assert err <= act_tol, f"{name}: relative error {err:.3e} > {act_tol}"
     # ---- heads
     pred, off, reg = eng.debug_predictions()
     o_off, o_reg = H.oracle_features(tr, "offset"), H.oracle_features(tr, "regression")
-    assert H.rel_err(off, o_off[g2o[0]]) <= 5e-5
-    assert H.rel_err(reg, o_reg[g2o[0]][:, 0]) <= 5e-5
+    assert H.rel_err(off, o_off[g2o[0]]) <= 2.5 * act_tol
+    assert H.rel_err(reg, o_reg[g2o[0]][:, 0]) <= 2.5 * act_tol
     # ---- iteration result: same rows, same order
     Pg, Dg = eng.result()
     assert Pg.shape == Po.shape
-    assert np.max(np.abs(Pg.astype(np.float64) - Po)) <= POS_TOL + 2e-5 * float(np.max(np.abs(Do)))
-    assert H.rel_err(Dg, Do) <= DISP_TOL
+    assert np.max(np.abs(Pg.astype(np.float64) - Po)) <= POS_TOL[conv_mode if conv_mode in POS_TOL else 0]
+    assert H.rel_err(Dg, Do) <= DISP_TOL[conv_mode if conv_mode in DISP_TOL else 0]
     return eng, st, (Po, Do, tr)
 
 
-def test_single_iteration_real_weights(leafoff_state, small_tree):
-    check_iteration(leafoff_state, small_tree)
+@pytest.mark.parametrize("mode", list(MODES))
+def test_single_iteration_real_weights(leafoff_state, small_tree, mode):
+    check_iteration(leafoff_state, small_tree, conv_mode=MODES[mode])
 
 
-def test_single_iteration_random_weights(random_state, small_tree):
-    check_iteration(random_state, small_tree)
+@pytest.mark.parametrize("mode", list(MODES))
+def test_single_iteration_random_weights(random_state, small_tree, mode):
+    check_iteration(random_state, small_tree, conv_mode=MODES[mode])
+
+
+def test_single_pass_tf32_mode(leafoff_state, small_tree):
+    """Reduced-precision mode (App. D.4): integers still bit-exact, activations within 1e-3 of the tensor scale... """
+    check_iteration(leafoff_state, small_tree, conv_mode=3, check_float=False)
 
 
 def test_ragged_batches(random_state):
