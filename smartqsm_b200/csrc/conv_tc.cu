@@ -129,12 +129,20 @@ struct TcArgs {
     int n_tiles;
 };
 
-constexpr int kTcStages = 4;          // shared-memory ring (A hi/lo + B hi/lo per stage)
+constexpr int kTcMaxStages = 6;       // shared-memory ring (A hi/lo + B hi/lo per stage), as many as fit 227 KB
 constexpr int kTcPrefetch = 3;        // chunks of gather loads in flight per producer thread (registers)
-constexpr int kTcProducers = 128;     // warps 0-3: gather; thread t owns tile row t
-constexpr int kTcEpilogue = 128;      // warps 4-7: TMEM -> registers -> global; thread owns tile row t-128
-constexpr int kTcThreads = kTcProducers + kTcEpilogue + 32;   // warp 8: MMA issuer
+constexpr int kTcGroups = 2;          // producer groups; group g gathers chunks g, g+G, ... (thread-level parallelism:
+                                      // one warp per SM sub-partition cannot hide its own issue latencies)
+constexpr int kTcProducers = 128;     // threads per producer group; thread t owns tile row t
+constexpr int kTcProdWarps = kTcGroups * 4;
+constexpr int kTcEpilogue = 128;      // next 4 warps: TMEM -> registers -> global; thread owns one tile row
+constexpr int kTcThreads = kTcGroups * kTcProducers + kTcEpilogue + 32;   // last warp: MMA issuer
 constexpr uint32_t kTmemCols = 128;   // two accumulator stages of 64 columns
+
+__host__ __device__ constexpr int tc_stages(int np) {
+    int fit = (227 * 1024 - 2048) / (2 * 128 * 128 + 2 * np * 128);
+    return fit > kTcMaxStages ? kTcMaxStages : fit;
+}
 
 template <int CI, int CO, int KV, bool CAT, bool PRECISE>
 __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant__ TcArgs a) {
@@ -144,49 +152,54 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
     constexpr int A_BYTES = 128 * 128;
     constexpr int B_BYTES = NP * 128;
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    constexpr int kTcStages = tc_stages(NP);
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     static_assert(CI % 8 == 0 && NP <= 64 && B_BYTES % 1024 == 0, "tile shape");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B needs 1024 B alignment
-    __shared__ __align__(8) uint64_t bars[2 * kTcStages + 4];
+    __shared__ __align__(8) uint64_t bars[2 * kTcMaxStages + 4];
     __shared__ uint32_t tmem_slot;
 
     const int t = threadIdx.x;
     const int warp = t >> 5;
-    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kTcStages]);
-    const uint32_t tfull0 = smem_u32(&bars[2 * kTcStages]), tempty0 = smem_u32(&bars[2 * kTcStages + 2]);
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kTcMaxStages]);
+    const uint32_t tfull0 = smem_u32(&bars[2 * kTcMaxStages]), tempty0 = smem_u32(&bars[2 * kTcMaxStages + 2]);
 
     if (t == 0) {
         for (int s = 0; s < kTcStages; ++s) { mbar_init(full0 + 8 * s, kTcProducers); mbar_init(empty0 + 8 * s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, kTcEpilogue); }
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(smem_u32(&tmem_slot), kTmemCols);
+    if (warp == kTcProdWarps + 4) tmem_alloc(smem_u32(&tmem_slot), kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
-    if (warp < 4) {
+    if (warp < kTcProdWarps) {
         // ===================== producers: gather -> TF32 hi/lo split -> swizzled smem tiles =====================
         // One chunk = 8 float4 per thread.  kTcPrefetch chunks are kept in flight in registers so that the
         // latency of the gather (L2 / HBM) overlaps with the stores of earlier chunks.
         const int n_my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
         const int total = n_my_tiles * NCH;               // chunk sequence of this CTA
+        const int grp = warp >> 2;                        // producer group
+        const int tp = t & (kTcProducers - 1);            // thread inside the group = tile row
+        const int my_total = (total - grp + kTcGroups - 1) / kTcGroups;   // chunks grp, grp+G, ... of that sequence
         // Lane l of a warp copies piece (l & 7) of tile rows (l >> 3) + 4m, m = 0..7: the eight lanes of a row
         // move one contiguous 128 B (or 2 x 64 B) span.  Rulebook entries are loaded by the lane that owns the
         // row, RI-1 chunks ahead (the only register loads left), and travel by shuffle.
         constexpr int KPC = (CI >= 32) ? 1 : 32 / CI;    // kernel offsets covered by one chunk
-        constexpr int RI = 4;
-        const int lane = t & 31;
+        constexpr int RI = 8;
+        const int lane = tp & 31;
         const int piece = lane & 7;
         const uint32_t smem_base = smem_u32(smem);
         int ibuf[RI][KPC];
-        auto issue_idx = [&](int c, int* nb) {
+        auto issue_idx = [&](int i, int* nb) {            // i-th chunk of this group
+            const int c = grp + i * kTcGroups;
             const int tile = (int)blockIdx.x + (c / NCH) * (int)gridDim.x;
             const int j = c % NCH;
-            const int row = tile * 128 + t;
+            const int row = tile * 128 + tp;
             #pragma unroll
             for (int q = 0; q < KPC; ++q) {
                 const int k = (j * 32) / CI + q;
@@ -197,12 +210,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
         };
         #pragma unroll
         for (int d = 0; d < RI - 1; ++d)
-            if (d < total) issue_idx(d, ibuf[d]);
-        for (int c0 = 0; c0 < total; c0 += RI) {
+            if (d < my_total) issue_idx(d, ibuf[d]);
+        for (int i0 = 0; i0 < my_total; i0 += RI) {
             #pragma unroll
             for (int u = 0; u < RI; ++u) {
-                const int c = c0 + u;
-                if (c < total) {
+                const int i = i0 + u;
+                if (i < my_total) {
+                    const int c = grp + i * kTcGroups;
                     const uint32_t stage = (uint32_t)c % kTcStages, ph = ((uint32_t)c / kTcStages) & 1u;
                     const int j = c % NCH;
                     const uint32_t sA_hi = smem_base + stage * STAGE_BYTES;
@@ -226,7 +240,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
                         bool second = false;
                         if (CAT) { second = ci >= CI / 2; eoff = nn * (CI / 2) + (second ? ci - CI / 2 : ci); }
                         else eoff = nn * CI + ci;
-                        const uint32_t rt = (uint32_t)(t & ~31) + (uint32_t)rl;
+                        const uint32_t rt = (uint32_t)(tp & ~31) + (uint32_t)rl;
                         const uint32_t off = rt * 128u + (uint32_t)((piece ^ (int)(rt & 7u)) << 4);
                         const uint32_t sz = on ? 16u : 0u;
                         cp_async16(sA_hi + off, (second ? a.inB : a.inA) + eoff, sz);
@@ -236,19 +250,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
                         const float* src = a.wimg + (size_t)j * (2 * B_BYTES / 4);
                         constexpr int NPIECE = (PRECISE ? 2 : 1) * B_BYTES / 16;
                         #pragma unroll
-                        for (int i = 0; i < (NPIECE + kTcProducers - 1) / kTcProducers; ++i) {
-                            int q = t + i * kTcProducers;
+                        for (int w = 0; w < (NPIECE + kTcProducers - 1) / kTcProducers; ++w) {
+                            int q = tp + w * kTcProducers;
                             if (q < NPIECE) cp_async16(sB + 16u * q, src + 4 * q, 16u);
                         }
                     }
                     cp_async_arrive(full0 + 8 * stage);   // one of the 128 arrivals, fires when this thread's copies landed
-                    if (c + RI - 1 < total) issue_idx(c + RI - 1, ibuf[(u + RI - 1) % RI]);
+                    if (i + RI - 1 < my_total) issue_idx(i + RI - 1, ibuf[(u + RI - 1) % RI]);
                 }
             }
         }
-    } else if (warp < 8) {
+    } else if (warp < kTcProdWarps + 4) {
         // ===================== epilogue: TMEM -> registers -> residual / select -> global =====================
-        const int te = t - kTcProducers;                  // tile row, also the TMEM lane
+        const int te = t - kTcGroups * kTcProducers;      // tile row, also the TMEM lane
         uint32_t tile_it = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tile_it) {
             const uint32_t as = tile_it & 1u, aph = (tile_it >> 1) & 1u;
@@ -310,7 +324,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == kTcProdWarps + 4) {
         __syncwarp();
         tmem_dealloc(tmem_base, kTmemCols);
     }
@@ -380,7 +394,7 @@ static void launch_tc(Ctx& cx, const TcArgs& a0, bool precise) {
     if (a.n_out <= 0) return;
     a.n_tiles = div_up(a.n_out, 128);
     constexpr int NP = CO < 16 ? 16 : CO;
-    constexpr size_t smem = (size_t)kTcStages * (2 * 128 * 128 + 2 * NP * 128) + 1024;
+    constexpr size_t smem = (size_t)tc_stages(NP) * (2 * 128 * 128 + 2 * NP * 128) + 1024;
     int grid = std::min(a.n_tiles, kNumSMs);
     if (precise) {
         auto kern = k_conv_tc<CI, CO, KV, CAT, true>;

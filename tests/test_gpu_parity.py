@@ -209,6 +209,44 @@ def test_full_run_with_chamfer_monitor(leafoff_state):
     assert np.array_equal(e_g, e_o)
 
 
+@pytest.mark.parametrize("name", ["random", "leafoff", "faces"])
+def test_against_reference_golden_vectors(name):
+    """tests/golden/contraction_*.npz come out of the reference's own driver (make_golden.py).  Each thunk is
+    replayed on the GPU from the golden state of the previous thunk: same row count and order, floats within
+    the fp32-FFMA tolerance, Chamfer value and accept/reject decision identical."""
+    import os
+    from oracle import weights
+    from smartqsm_b200._lib import Engine
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"contraction_{name}.npz"))
+    if name == "leafoff":
+        if weights.blob_path("leafoff") is None:
+            pytest.skip("reference checkpoint blob not present")
+        state = weights.load_state("leafoff", allow_random=False)
+    else:
+        state = ON.random_state(seed=7)
+    sizes, cds = g["sizes"], g["chamfer"]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    prev_P = g["points"].astype(np.float32)
+    prev_D = np.zeros_like(prev_P)
+    prev_cd = np.inf
+    for i in range(len(sizes)):
+        eng = Engine(batch_size=int(g["batch_size"]), monitored_by_chamfer_distance=True, conv_mode=1)
+        eng.load_state_dict(state)
+        eng.set_state(prev_P, prev_D)
+        st = eng.contract_step()
+        gP, gD = g["P"][offs[i]:offs[i + 1]], g["D"][offs[i]:offs[i + 1]]
+        accepted_ref = not (i > 0 and np.array_equal(gP, g["P"][offs[i - 1]:offs[i]]) and cds[i] == cds[i - 1])
+        if accepted_ref:
+            P, D = eng.result()
+            assert P.shape == gP.shape
+            assert np.max(np.abs(P - gP)) <= 2e-6 and H.rel_err(D, gD) <= 1e-5
+            assert abs(st["chamfer"] - cds[i]) <= 1e-9 * cds[i]
+            assert st["chamfer"] <= prev_cd
+            prev_P, prev_D, prev_cd = gP, gD, cds[i]
+        else:
+            assert st["chamfer"] > prev_cd * (1 - 1e-9)      # the reference rejected this thunk
+
+
 def test_latched_run_matches_unlatched(leafoff_state):
     from smartqsm_b200.core_algorithms import SpconvBasedContraction
     from smartqsm_b200.synthetic import make_tree
