@@ -13,6 +13,7 @@
 // the weights of the current offsets from shared memory as warp-broadcast float4 reads.  Residual
 // add, skip-concat (two input pointers) and the per-batch "did not descend" select are fused in.
 #include "engine.h"
+#include <algorithm>
 #include <cstring>
 
 namespace sqsm {
@@ -139,6 +140,68 @@ __global__ void __launch_bounds__(256) k_conv(ConvArgs a) {
             *reinterpret_cast<float4*>(a.out + o + 4 * q) = r;
         }
     }
+}
+
+// SparseInverseConv3d(k=2): every fine row has exactly one (parent, kernel offset) pair, so
+// out[i] = W[koff[i]] . bnrelu(in_c[parent[i]]) (zeros when the voxel did not survive the down-sample).
+// Thread = one row x 8 output channels; the 8 weight matrices sit in shared memory.
+template <int CI, int CO>
+__global__ void __launch_bounds__(256) k_upconv(const float* __restrict__ in, const int32_t* __restrict__ parent,
+                                                const int32_t* __restrict__ koff, const float* __restrict__ w,
+                                                const float* __restrict__ bn, float* __restrict__ out, int n) {
+    constexpr int SL = CO / 8;                       // channel slices per row
+    extern __shared__ __align__(16) float smem[];
+    float* sbn = smem;                               // [2][CI]
+    float* sw = smem + 2 * CI;                       // [8][CI*CO + 8]: 32 B of padding per offset so that lanes holding
+                                                     // different kernel offsets read different shared-memory banks
+    constexpr int KS = CI * CO + 8;
+    for (int i = threadIdx.x; i < 2 * CI; i += 256) sbn[i] = bn[i];
+    for (int i = threadIdx.x; i < 8 * CI * CO / 4; i += 256) {
+        const int k = i / (CI * CO / 4), r = i % (CI * CO / 4);
+        reinterpret_cast<float4*>(sw + (size_t)k * KS)[r] = reinterpret_cast<const float4*>(w)[i];
+    }
+    __syncthreads();
+    // persistent blocks: the 8 weight matrices are staged once per block, not once per 256 rows
+    const int64_t total = (int64_t)n * SL;
+    for (int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x; g < total; g += (int64_t)gridDim.x * 256) {
+    const int row = (int)(g / SL), sl = (int)(g % SL);
+    const int p = parent[row];
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (p >= 0) {
+        const float* wk = sw + (size_t)koff[row] * KS + sl * 8;
+        const float4* src = reinterpret_cast<const float4*>(in + (size_t)p * CI);
+        #pragma unroll
+        for (int c0 = 0; c0 < CI; c0 += 4) {
+            float4 x = __ldg(src + c0 / 4);
+            float v[4] = {x.x, x.y, x.z, x.w};
+            #pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const float a = fmaxf(fmaf(v[cc], sbn[c0 + cc], sbn[CI + c0 + cc]), 0.0f);
+                const float4 w0 = *reinterpret_cast<const float4*>(wk + (size_t)(c0 + cc) * CO);
+                const float4 w1 = *reinterpret_cast<const float4*>(wk + (size_t)(c0 + cc) * CO + 4);
+                acc[0] = fmaf(a, w0.x, acc[0]); acc[1] = fmaf(a, w0.y, acc[1]); acc[2] = fmaf(a, w0.z, acc[2]);
+                acc[3] = fmaf(a, w0.w, acc[3]); acc[4] = fmaf(a, w1.x, acc[4]); acc[5] = fmaf(a, w1.y, acc[5]);
+                acc[6] = fmaf(a, w1.z, acc[6]); acc[7] = fmaf(a, w1.w, acc[7]);
+            }
+        }
+    }
+    float4* dst = reinterpret_cast<float4*>(out + (size_t)row * CO + sl * 8);
+    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+}
+
+template <int CI, int CO>
+static void launch_upconv(Ctx& cx, const ConvW& w, const float* in, const int32_t* parent, const int32_t* koff, float* out,
+                          int64_t n) {
+    if (n <= 0) return;
+    const size_t smem = (size_t)(2 * CI + 8 * (CI * CO + 8)) * 4;
+    auto kern = k_upconv<CI, CO>;
+    if (smem > 48 * 1024) SQSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_sm = smem > 48 * 1024 ? 2 : 6;
+    const int grid = std::min<int64_t>(div_up(n * (CO / 8), 256), (int64_t)kNumSMs * per_sm);
+    kern<<<grid, 256, smem, cx.st>>>(in, parent, koff, w.w, w.bn, out, (int)n);
+    cx.launches++;
 }
 
 constexpr int kSmemBudget = 96 * 1024;
@@ -452,7 +515,10 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
         {
             ProfScope pt(cx, "down_up", 4.0 * (lv[l + 1].n * kPlanes[l + 1] + n * c) + 4.0 * n,
                          2.0 * (double)n * c * kPlanes[l + 1]);
-            conv_any(cx, nw, L + ".up", false, cur.p, nullptr, lv[l].inv.p, up.p, n, lv[l + 1].n);
+            const ConvW& wu = nw.conv.at(L + ".up");
+            if (l == 0) launch_upconv<16, 8>(cx, wu, cur.p, lv[l].parent.p, lv[l].koff.p, up.p, n);
+            else if (l == 1) launch_upconv<32, 16>(cx, wu, cur.p, lv[l].parent.p, lv[l].koff.p, up.p, n);
+            else launch_upconv<64, 32>(cx, wu, cur.p, lv[l].parent.p, lv[l].koff.p, up.p, n);
         }
         {   // blocks_tail on cat(enc, up); rows of batches that did not descend keep `enc`
             ProfScope pt(cx, lvl_family(l), 4.0 * n * (2 * c + c) * 2 + 4.0 * n * (c + c) + 2.0 * 4.0 * 27 * n + 4.0 * n * c,

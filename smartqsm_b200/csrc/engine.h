@@ -33,7 +33,6 @@ struct LevelTables {
     DBuf<int32_t>  parent;              // [n]      coarse row or -1              (levels 0..2)
     DBuf<int32_t>  koff;                // [n]      kz*4+ky*2+kx                  (levels 0..2)
     DBuf<int32_t>  child;               // [8][n_next] fine row or -1 (down conv, output-stationary)
-    DBuf<int32_t>  inv;                 // [8][n]   parent if koff==k else -1 (inverse conv)
     DBuf<uint8_t>  row_desc;            // [n] 1 if the row's batch descended below this level
     DBuf<int32_t>  shape;               // [n_batches][3] spatial shape (z,y,x) of this level per batch
     DBuf<int32_t>  desc;                // [n_batches] batch descended from this level

@@ -151,6 +151,23 @@ __global__ void __launch_bounds__(256) k_voxel_mean(double* __restrict__ sum, co
     sum[3 * r + 2] = __ddiv_rn(sum[3 * r + 2], c);
 }
 
+// voxel means relative to the origin of their own brick, float32 (screening copy for the NN search)
+__global__ void __launch_bounds__(256) k_local_means(const Brick* __restrict__ bricks, int n_bricks, const double* __restrict__ mean,
+                                                     const __grid_constant__ GridParams g, float4* __restrict__ loc) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = t >> 5, lane = t & 31;
+    if (b >= n_bricks) return;
+    const uint64_t key = bricks[b].key;
+    const double edge = 8.0 * g.voxel;
+    const double ox = g.mn[0] + (double)key_x(key) * edge, oy = g.mn[1] + (double)key_y(key) * edge,
+                 oz = g.mn[2] + (double)key_z(key) * edge;
+    const int base = bricks[b].base, n = bricks[b].count;
+    for (int i = lane; i < n; i += 32) {
+        const size_t r = (size_t)(base + i);
+        loc[r] = make_float4((float)(mean[3 * r] - ox), (float)(mean[3 * r + 1] - oy), (float)(mean[3 * r + 2] - oz), 0.f);
+    }
+}
+
 // For every brick of map A: (first row, count) of the 27 bricks of map B around the same coordinates.
 __global__ void __launch_bounds__(256) k_cross_neighbours(const Brick* __restrict__ A, int nA, BrickHash hB,
                                                           const Brick* __restrict__ B, int2* __restrict__ abn) {
@@ -178,9 +195,13 @@ __global__ void __launch_bounds__(256) k_cross_neighbours(const Brick* __restric
 // exceeds that bound keeps growing rings of bricks (hash probes) until it does not - exact 1-NN like the
 // KD-tree search of Open3D's compute_point_cloud_distance.
 constexpr int kNNThreads = 256;
+// visiting order of the 27 bricks: centre, 6 faces, 12 edges, 8 corners (nearest first -> best pruning)
+__constant__ int c_nn_order[27] = {13, 4, 10, 12, 14, 16, 22, 1, 3, 5, 7, 9, 11, 15, 17, 19, 21, 23, 25,
+                                   0, 2, 6, 8, 18, 20, 24, 26};
 __global__ void __launch_bounds__(kNNThreads) k_nn_sqdist(const Brick* __restrict__ A, int nA, const double* __restrict__ meanA,
                                                           const int2* __restrict__ abn, BrickHash hB,
                                                           const Brick* __restrict__ B, const double* __restrict__ meanB,
+                                                          const float4* __restrict__ locB,
                                                           const __grid_constant__ GridParams g, int max_ring,
                                                           double* __restrict__ acc, unsigned long long* __restrict__ n_fallback) {
     __shared__ double s_red[kNNThreads / 32];
@@ -195,6 +216,7 @@ __global__ void __launch_bounds__(kNNThreads) k_nn_sqdist(const Brick* __restric
         const int nq = A[a].count, qbase = A[a].base;
         const uint64_t key = A[a].key;
         const int2 mine = abn[(size_t)a * 32 + lane];
+        const unsigned present = __ballot_sync(0xFFFFFFFFu, lane < 27 && mine.y > 0);
         const int bz = (int)key_z(key), by = (int)key_y(key), bx = (int)key_x(key);
         int S = 1;                                          // lanes per query
         if (nq <= 16) { int p2 = 1; while (p2 < nq) p2 <<= 1; S = 32 / p2; }
@@ -211,23 +233,38 @@ __global__ void __launch_bounds__(kNNThreads) k_nn_sqdist(const Brick* __restric
             // offset of the query inside its brick (x, y, z)
             const double lx = qx - (g.mn[0] + (double)bx * edge), ly = qy - (g.mn[1] + (double)by * edge),
                          lz = qz - (g.mn[2] + (double)bz * edge);
+            const float qlx = (float)lx, qly = (float)ly, qlz = (float)lz, edge_f = (float)edge;
+            // per-axis gaps to the neighbouring bricks in float32 (pruning bound only; made conservative by `slack`)
+            const float gm[3] = {fmaxf((float)(lx - slack), 0.f), fmaxf((float)(ly - slack), 0.f), fmaxf((float)(lz - slack), 0.f)};
+            const float gp[3] = {fmaxf((float)(edge - lx - slack), 0.f), fmaxf((float)(edge - ly - slack), 0.f),
+                                 fmaxf((float)(edge - lz - slack), 0.f)};
             double best = 1e300;
             #pragma unroll 1
             for (int step = 0; step < 27; ++step) {
-                const int nb = (step == 0) ? 13 : (step <= 13 ? step - 1 : step);      // centre brick first
+                const int nb = c_nn_order[step];                                     // centre, faces, edges, corners
+                if (!((present >> nb) & 1u)) continue;                               // warp-uniform
                 const int2 rc = make_int2(__shfl_sync(0xFFFFFFFFu, mine.x, nb), __shfl_sync(0xFFFFFFFFu, mine.y, nb));
-                if (rc.y == 0) continue;                                             // warp-uniform
                 const int dz = nb / 9 - 1, dy = (nb / 3) % 3 - 1, dx = nb % 3 - 1;
-                double gx = dx == 0 ? 0.0 : (dx < 0 ? lx : edge - lx), gy = dy == 0 ? 0.0 : (dy < 0 ? ly : edge - ly),
-                       gz = dz == 0 ? 0.0 : (dz < 0 ? lz : edge - lz);
-                gx = fmax(gx - slack, 0.0); gy = fmax(gy - slack, 0.0); gz = fmax(gz - slack, 0.0);
-                const double lb2 = gx * gx + gy * gy + gz * gz;
-                if (__all_sync(0xFFFFFFFFu, !valid || best <= lb2)) continue;
+                const float gx = dx == 0 ? 0.f : (dx < 0 ? gm[0] : gp[0]), gy = dy == 0 ? 0.f : (dy < 0 ? gm[1] : gp[1]),
+                            gz = dz == 0 ? 0.f : (dz < 0 ? gm[2] : gp[2]);
+                const float lb2 = (gx * gx + gy * gy + gz * gz) * 0.999999f;       // never above the true bound
+                if (__all_sync(0xFFFFFFFFu, !valid || best <= (double)lb2)) continue;
+                // float32 screening in brick-local coordinates (|coordinate| < 3 brick edges, error ~2e-6 relative on
+                // d^2); every candidate that could beat the current best is re-evaluated in float64
                 const double* c = meanB + 3 * (size_t)rc.x;
+                const float4* cl = locB + (size_t)rc.x;
+                const float sx = qlx - (float)dx * edge_f, sy = qly - (float)dy * edge_f, sz = qlz - (float)dz * edge_f;
                 double bl = best;
+                float blf = (bl < 1e30) ? (float)bl * 1.00002f : 3.0e38f;
                 for (int i = sl; i < rc.y; i += S) {
-                    double ex = qx - c[3 * i], ey = qy - c[3 * i + 1], ez = qz - c[3 * i + 2];
-                    bl = fmin(bl, ex * ex + ey * ey + ez * ez);
+                    const float4 p = __ldg(cl + i);
+                    const float fx = sx - p.x, fy = sy - p.y, fz = sz - p.z;
+                    const float d2f = fx * fx + fy * fy + fz * fz;
+                    if (d2f <= blf) {
+                        double ex = qx - c[3 * i], ey = qy - c[3 * i + 1], ez = qz - c[3 * i + 2];
+                        bl = fmin(bl, ex * ex + ey * ey + ez * ez);
+                        blf = (float)bl * 1.00002f;
+                    }
                 }
                 for (int d = 1; d < S; d <<= 1) bl = fmin(bl, __shfl_xor_sync(0xFFFFFFFFu, bl, d));
                 best = bl;
@@ -274,6 +311,7 @@ __global__ void __launch_bounds__(kNNThreads) k_nn_sqdist(const Brick* __restric
 struct VoxelMeans {
     GridMap gm;
     DBuf<double> mean;         // [rows][3]
+    DBuf<float4> loc;          // [rows] mean relative to its brick origin, float32
 };
 
 static void voxel_means(Ctx& cx, const float* d_P, int64_t n, const double mn[3], double voxel, VoxelMeans& vm) {
@@ -287,7 +325,10 @@ static void voxel_means(Ctx& cx, const float* d_P, int64_t n, const double mn[3]
     cnt.zero();
     k_voxel_accumulate<<<div_up(n, 256), 256, 0, st>>>(d_P, vm.gm.pt_row.p, n, vm.mean.p, cnt.p);
     k_voxel_mean<<<div_up(rows, 256), 256, 0, st>>>(vm.mean.p, cnt.p, rows);
-    cx.launches += 2;
+    vm.loc.alloc(rows, st);
+    k_local_means<<<div_up((int64_t)vm.gm.map.n_bricks * 32, 256), 256, 0, st>>>(vm.gm.map.bricks.p, vm.gm.map.n_bricks, vm.mean.p,
+                                                                                 vm.gm.g, vm.loc.p);
+    cx.launches += 3;
 }
 
 double chamfer_distance(Ctx& cx, const float* d_P, int64_t np, const float* d_Q, int64_t nq, double voxel) {
@@ -321,9 +362,9 @@ double chamfer_distance(Ctx& cx, const float* d_P, int64_t np, const float* d_Q,
                                                                       A.gm.map.bricks.p, ban.p);
     int gA = std::min(div_up(nA, kNNThreads / 32), kNumSMs * 8), gB = std::min(div_up(nB, kNNThreads / 32), kNumSMs * 8);
     k_nn_sqdist<<<gA, kNNThreads, 0, st>>>(A.gm.map.bricks.p, nA, A.mean.p, abn.p, B.gm.map.view(), B.gm.map.bricks.p,
-                                           B.mean.p, A.gm.g, max_ring, acc.p, nfb.p);
+                                           B.mean.p, B.loc.p, A.gm.g, max_ring, acc.p, nfb.p);
     k_nn_sqdist<<<gB, kNNThreads, 0, st>>>(B.gm.map.bricks.p, nB, B.mean.p, ban.p, A.gm.map.view(), A.gm.map.bricks.p,
-                                           A.mean.p, A.gm.g, max_ring, acc.p + 1, nfb.p + 1);
+                                           A.mean.p, A.loc.p, A.gm.g, max_ring, acc.p + 1, nfb.p + 1);
     cx.launches += 4;
     if (Trace::enabled()) {
         auto f = nfb.to_host();

@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(256) k_down_entries(const Brick* __restrict__ 
 __global__ void __launch_bounds__(256) k_down_tables(const Brick* __restrict__ cbricks, const int32_t* __restrict__ ent_brick,
                                                      const uint16_t* __restrict__ ent_pos, const int32_t* __restrict__ koff,
                                                      int64_t n, int64_t n_next, int32_t* __restrict__ parent,
-                                                     int32_t* __restrict__ child, int32_t* __restrict__ inv) {
+                                                     int32_t* __restrict__ child) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     int b = ent_brick[r];
@@ -543,7 +543,6 @@ __global__ void __launch_bounds__(256) k_down_tables(const Brick* __restrict__ c
     if (p >= 0) {
         int k = koff[r];
         child[(size_t)k * n_next + p] = (int32_t)r;
-        inv[(size_t)k * n + r] = p;
     }
 }
 
@@ -583,8 +582,6 @@ bool build_down(Ctx& cx, LevelTables& L, LevelTables& Ln, int batch0, int n_batc
     }
     Ln.n = Ln.map.n_rows;
     L.parent.alloc(n, st);
-    L.inv.alloc(8 * n, st);
-    L.inv.fill_ff();
     if (Ln.n == 0) {
         L.parent.fill_ff();
         return false;
@@ -592,7 +589,7 @@ bool build_down(Ctx& cx, LevelTables& L, LevelTables& Ln, int batch0, int n_batc
     L.child.alloc(8 * Ln.n, st);
     L.child.fill_ff();
     k_down_tables<<<div_up(n, 256), 256, 0, st>>>(Ln.map.bricks.p, ent_brick.p, ent_pos.p, L.koff.p, n, Ln.n, L.parent.p,
-                                                  L.child.p, L.inv.p);
+                                                  L.child.p);
     cx.launches++;
     Ln.row_brick.alloc(Ln.n, st);
     Ln.row_pos.alloc(Ln.n, st);

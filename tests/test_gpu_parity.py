@@ -194,7 +194,8 @@ def test_full_run_with_chamfer_monitor(leafoff_state):
     assert acc_o == acc_g
     for ho, hg in zip(o.history, g.history):
         assert abs(ho["n_out"] - hg["n_out"]) <= max(2, ho["n_out"] // 2000)       # sub-voxel float flips only
-        assert abs(ho["chamfer"] - hg["chamfer"]) <= 1e-6 * ho["chamfer"] + 1e-12 or ho["n_out"] != hg["n_out"]
+        # each side evaluates the monitor on its own float32 state (positions differ by ~1e-6 m)
+        assert abs(ho["chamfer"] - hg["chamfer"]) <= 2e-5 * ho["chamfer"] + 1e-12 or ho["n_out"] != hg["n_out"]
     out_o, out_g = o.output(), g.output()
     if out_o["contracted_points"].shape == out_g["contracted_points"].shape:
         assert np.max(np.abs(out_o["contracted_points"] - out_g["contracted_points"])) <= 1e-4
@@ -240,7 +241,9 @@ def test_against_reference_golden_vectors(name):
             P, D = eng.result()
             assert P.shape == gP.shape
             assert np.max(np.abs(P - gP)) <= 2e-6 and H.rel_err(D, gD) <= 1e-5
-            assert abs(st["chamfer"] - cds[i]) <= 1e-9 * cds[i]
+            # the monitor is evaluated on the GPU's own float32 result (<= 2e-6 m from the golden one); the kernel
+            # itself is checked to 1e-9 in test_chamfer_value
+            assert abs(st["chamfer"] - cds[i]) <= 2e-5 * cds[i]
             assert st["chamfer"] <= prev_cd
             prev_P, prev_D, prev_cd = gP, gD, cds[i]
         else:
