@@ -291,19 +291,28 @@ def main_b200(args):
         hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") \
             else (6650.0, "fallback (B200_PROFILING.md)")
         fams = {k: v for k, v in prof.items() if v["launches"] > 0 and v["ms"] > 0}
-        dom = max(fams, key=lambda k: fams[k]["ms"]) if fams else None
+        kernels = {k: v for k, v in fams.items() if k.startswith("conv_")}     # one entry per convolution kernel shape
+        dom = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
         roofline = None
         if dom:
             f = fams[dom]
             ach = f["bytes"] / (f["ms"] * 1e-3) / 1e9
+            traffic = None
+            try:    # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture of this command
+                tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+                traffic = tr.get(args.workload, {}).get(dom)
+            except Exception:
+                pass
             roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                        "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                         "avg_launch_ms": f["ms"] / f["launches"], "launches": f["launches"],
                         "algorithmic_bytes_per_launch": f["bytes"] / f["launches"],
                         "gflops_fp32": f["flops"] / (f["ms"] * 1e-3) / 1e9 if f["flops"] else None,
                         "share_of_step": f["ms"] / dev_ms}
         fam_table = {k: {"ms_per_step": v["ms"] / args.steps, "GB/s": v["bytes"] / (v["ms"] * 1e-3) / 1e9,
                          "launches_per_step": v["launches"] / args.steps} for k, v in sorted(fams.items())}
+        # families nest: stage families (tiling, voxelise, rulebook, subm_l*, down_up, heads, chamfer, skeletal,
+        # radius_graph) partition the step; conv_* / cd_* / rb_* / vx_* are per-kernel views inside them
         acc = sum(1 for s in stats if s["accepted"])
         line = {
             "metric": "points/sec", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,

@@ -37,7 +37,7 @@ struct ProfScope {
     Ctx& cx; ProfRec r; bool on;
     ProfScope(Ctx& c, const char* fam, double bytes, double flops) : cx(c), on(c.prof_on) {
         if (!on) return;
-        r.fam = cx.family(fam); r.bytes = bytes; r.flops = flops; r.launches = cx.launches;
+        r.fam = cx.family(std::string(fam)); r.bytes = bytes; r.flops = flops; r.launches = cx.launches;
         cudaEventCreate(&r.a); cudaEventCreate(&r.b);
         cudaEventRecord(r.a, cx.st);
     }

@@ -437,22 +437,33 @@ static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, boo
                      const float* sel_src = nullptr, const uint8_t* sel_flag = nullptr) {
     const ConvW& w = nw.conv.at(name);
     if (n_out <= 0) return;
-    if (nw.mode != 0 && w.wimg && w.co >= nw.tc_min_co) {
+    const bool use_tc = nw.mode != 0 && w.wimg && w.co >= nw.tc_min_co;
+    // per-kernel scope: algorithmic bytes of SURVEY 8(d): features in + out, rulebook entries, residual re-read
+    char fam[64];
+    snprintf(fam, sizeof(fam), "conv_%s_ci%d_co%d_k%d", use_tc ? "tc" : "ffma", w.ci, w.co, w.kv);
+    const double alg_bytes = 4.0 * ((double)n_in * w.ci + (double)n_out * w.co) + 4.0 * (nbr ? (double)w.kv * n_out : 0.0) +
+                             (res ? 4.0 * (double)n_out * w.co : 0.0);
+    if (use_tc) {
         // activation + TF32 hi/lo split once per element, then the tensor-core implicit GEMM
         const bool precise = nw.mode == 1;
         const int ca = cat ? w.ci / 2 : w.ci;
         DBuf<float> a_hi(n_in * ca, cx.st), a_lo, b_hi, b_lo;
         if (precise) a_lo.alloc(n_in * ca, cx.st);
-        act_split(cx, inA, w.bn, ca, 0, w.ci, n_in, a_hi.p, a_lo.p);
-        if (cat) {
-            b_hi.alloc(n_in * ca, cx.st);
-            if (precise) b_lo.alloc(n_in * ca, cx.st);
-            act_split(cx, inB, w.bn, ca, ca, w.ci, n_in, b_hi.p, b_lo.p);
+        {
+            ProfScope pa(cx, "act_split", (double)n_in * w.ci * 4.0 * (precise ? 3 : 2), 0.0);
+            act_split(cx, inA, w.bn, ca, 0, w.ci, n_in, a_hi.p, a_lo.p);
+            if (cat) {
+                b_hi.alloc(n_in * ca, cx.st);
+                if (precise) b_lo.alloc(n_in * ca, cx.st);
+                act_split(cx, inB, w.bn, ca, ca, w.ci, n_in, b_hi.p, b_lo.p);
+            }
         }
+        ProfScope ps(cx, fam, alg_bytes, 0.0);
         if (conv_tc(cx, w.ci, w.co, w.kv, cat, a_hi.p, b_hi.p, a_lo.p, b_lo.p, nbr, w.wimg, res, sel_src, sel_flag, out, n_out,
                     precise))
             return;
     }
+    ProfScope ps(cx, fam, alg_bytes, 0.0);
     ConvArgs ar;
     ar.inA = inA; ar.inB = inB; ar.nbr = nbr; ar.w = w.w; ar.bn = w.bn; ar.res = res; ar.sel_src = sel_src;
     ar.sel_flag = sel_flag; ar.out = out; ar.n_out = (int)n_out; ar.kc = 0;
