@@ -39,9 +39,10 @@ typedef struct SqsmConfig {
                                            identical); 0: recompute like the reference does  */
     int32_t down_kernel_flip;           /* 0: k index = (z&1,y&1,x&1) (SURVEY App. A default) */
     int32_t conv_mode;                  /* arithmetic of the 16/32/64-channel convolutions:
-                                           0 = library default (2), 1 = fp32 FFMA everywhere,
+                                           0 = library default (4), 1 = fp32 FFMA everywhere,
                                            2 = tcgen05 3xTF32 split (fp32-class accuracy),
-                                           3 = tcgen05 single-pass TF32 (reduced precision, App. D.4) */
+                                           3 = tcgen05 single-pass TF32 (reduced precision, App. D.4),
+                                           4 = tcgen05 3xFP16 split (fp32-class; activations must stay < 3e4) */
     int32_t reserved[6];
 } SqsmConfig;
 

@@ -295,6 +295,7 @@ __global__ void __launch_bounds__(256) k_heads(const float* __restrict__ feat, c
 // ---------------------------------------------------------------------------------- weights
 
 std::vector<float> make_tc_weight_image(const float* w_kcico, int kv, int ci, int co);   // conv_tc.cu
+std::vector<float> make_tc_weight_image_f16(const float* w_kcico, int kv, int ci, int co);
 
 static const std::vector<float>& need(const std::map<std::string, std::vector<float>>& st, const std::string& k,
                                       size_t n) {
@@ -321,12 +322,12 @@ static void fold_bn(const std::map<std::string, std::vector<float>>& st, const s
 
 void net_upload(Ctx& cx, NetWeights& nw, const std::map<std::string, std::vector<float>>& st, bool down_flip) {
     std::vector<float> blob;
-    struct Pending { std::string name; size_t w_off, bn_off, img_off; bool has_bn, has_img; int ci, co, kv; };
+    struct Pending { std::string name; size_t w_off, bn_off, img_off, img16_off; bool has_bn, has_img; int ci, co, kv; };
     std::vector<Pending> pend;
     auto add_conv = [&](const std::string& name, const std::string& wkey, const std::string& bnkey, int ci, int co, int kv,
                         int ci_pad, bool flip) {
         const auto& W = need(st, wkey, (size_t)co * kv * ci);   // [co][k][ci]
-        Pending p{name, blob.size(), 0, 0, !bnkey.empty(), false, ci_pad, co, kv};
+        Pending p{name, blob.size(), 0, 0, 0, !bnkey.empty(), false, ci_pad, co, kv};
         blob.resize(blob.size() + (size_t)kv * ci_pad * co, 0.0f);
         for (int k = 0; k < kv; ++k)
             for (int c = 0; c < ci; ++c)
@@ -346,6 +347,10 @@ void net_upload(Ctx& cx, NetWeights& nw, const std::map<std::string, std::vector
             p.img_off = blob.size();
             p.has_img = true;
             blob.insert(blob.end(), img.begin(), img.end());
+            std::vector<float> img16 = make_tc_weight_image_f16(&blob[p.w_off], kv, ci_pad, co);
+            while (blob.size() % 64) blob.push_back(0.0f);
+            p.img16_off = blob.size();
+            blob.insert(blob.end(), img16.begin(), img16.end());
         }
         pend.push_back(p);
     };
@@ -366,7 +371,9 @@ void net_upload(Ctx& cx, NetWeights& nw, const std::map<std::string, std::vector
         }
         prefix += ".u";
     }
-    nw.blob.alloc((int64_t)blob.size(), cx.st);
+    nw.blob.alloc((int64_t)blob.size() + 4, cx.st);
+    nw.range_flag = reinterpret_cast<int*>(nw.blob.p + blob.size());     // FP16 range guard (last word of the blob)
+    SQSM_CUDA(cudaMemsetAsync(nw.range_flag, 0, sizeof(int), cx.st));
     SQSM_CUDA(cudaMemcpyAsync(nw.blob.p, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice, cx.st));
     SQSM_CUDA(cudaStreamSynchronize(cx.st));
     nw.conv.clear();
@@ -376,6 +383,7 @@ void net_upload(Ctx& cx, NetWeights& nw, const std::map<std::string, std::vector
         c.w = nw.blob.p + p.w_off;
         c.bn = p.has_bn ? nw.blob.p + p.bn_off : nullptr;
         c.wimg = p.has_img ? nw.blob.p + p.img_off : nullptr;
+        c.wimg16 = p.has_img ? nw.blob.p + p.img16_off : nullptr;
         nw.conv[p.name] = c;
     }
     // heads (App. A #48-51)
@@ -410,8 +418,11 @@ static void conv_dispatch(Ctx& cx, const ConvArgs& a) {
 // conv_tc.cu
 bool conv_tc(Ctx& cx, int ci, int co, int kv, bool cat, const float* inA, const float* inB, const float* inA_lo,
              const float* inB_lo, const int32_t* nbr, const float* wimg, const float* res, const float* sel_src,
-             const uint8_t* sel_flag, float* out, int64_t n_out, bool precise);
+             const uint8_t* sel_flag, float* out, int64_t n_out, bool precise, bool f16);
 void act_split(Ctx& cx, const float* in, const float* bn, int c, int bn_off, int bn_stride, int64_t n, float* hi, float* lo);
+void act_split_f16(Ctx& cx, const float* in, const float* bn, int c, int bn_off, int bn_stride, int64_t n, void* hi, void* lo,
+                   int* range_flag);
+std::vector<float> make_tc_weight_image_f16(const float* w_kcico, int kv, int ci, int co);
 
 static bool conv_ffma(Ctx& cx, const ConvW& w, bool cat, const ConvArgs& a) {
     const bool bn = w.bn != nullptr;
@@ -445,22 +456,27 @@ static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, boo
                              (res ? 4.0 * (double)n_out * w.co : 0.0);
     if (use_tc) {
         // activation + TF32 hi/lo split once per element, then the tensor-core implicit GEMM
-        const bool precise = nw.mode == 1;
+        const bool f16 = nw.mode == 3;
+        const bool precise = nw.mode == 1 || f16;
         const int ca = cat ? w.ci / 2 : w.ci;
-        DBuf<float> a_hi(n_in * ca, cx.st), a_lo, b_hi, b_lo;
-        if (precise) a_lo.alloc(n_in * ca, cx.st);
+        // FP16 operands take half the space of TF32 ones: allocate in float units either way
+        const int64_t elems = f16 ? (n_in * ca + 1) / 2 : n_in * ca;
+        DBuf<float> a_hi(elems, cx.st), a_lo, b_hi, b_lo;
+        if (precise) a_lo.alloc(elems, cx.st);
         {
-            ProfScope pa(cx, "act_split", (double)n_in * w.ci * 4.0 * (precise ? 3 : 2), 0.0);
-            act_split(cx, inA, w.bn, ca, 0, w.ci, n_in, a_hi.p, a_lo.p);
+            ProfScope pa(cx, "act_split", (double)n_in * w.ci * (f16 ? 8.0 : 4.0 * (precise ? 3 : 2)), 0.0);
+            if (f16) act_split_f16(cx, inA, w.bn, ca, 0, w.ci, n_in, a_hi.p, a_lo.p, nw.range_flag);
+            else act_split(cx, inA, w.bn, ca, 0, w.ci, n_in, a_hi.p, a_lo.p);
             if (cat) {
-                b_hi.alloc(n_in * ca, cx.st);
-                if (precise) b_lo.alloc(n_in * ca, cx.st);
-                act_split(cx, inB, w.bn, ca, ca, w.ci, n_in, b_hi.p, b_lo.p);
+                b_hi.alloc(elems, cx.st);
+                if (precise) b_lo.alloc(elems, cx.st);
+                if (f16) act_split_f16(cx, inB, w.bn, ca, ca, w.ci, n_in, b_hi.p, b_lo.p, nw.range_flag);
+                else act_split(cx, inB, w.bn, ca, ca, w.ci, n_in, b_hi.p, b_lo.p);
             }
         }
         ProfScope ps(cx, fam, alg_bytes, 0.0);
-        if (conv_tc(cx, w.ci, w.co, w.kv, cat, a_hi.p, b_hi.p, a_lo.p, b_lo.p, nbr, w.wimg, res, sel_src, sel_flag, out, n_out,
-                    precise))
+        if (conv_tc(cx, w.ci, w.co, w.kv, cat, a_hi.p, b_hi.p, a_lo.p, b_lo.p, nbr, f16 ? w.wimg16 : w.wimg, res, sel_src, sel_flag,
+                    out, n_out, precise, f16))
             return;
     }
     ProfScope ps(cx, fam, alg_bytes, 0.0);

@@ -24,6 +24,7 @@
 // TMA is not used for A: the rows of a tile come from arbitrary addresses (a gather), which is exactly
 // what TMA cannot express; the weight chunk is small and shared by all tiles (L2 resident).
 #include "engine.h"
+#include <cuda_fp16.h>
 #include <cstring>
 
 namespace sqsm {
@@ -69,6 +70,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// kind::f16 variant (FP16 operands, FP32 accumulation in TMEM); K = 16 elements = 32 bytes per instruction
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // mbarrier arrives when all previously issued MMAs of this thread have completed
@@ -144,16 +154,24 @@ __host__ __device__ constexpr int tc_stages(int np) {
     return fit > kTcMaxStages ? kTcMaxStages : fit;
 }
 
-template <int CI, int CO, int KV, bool CAT, bool PRECISE>
+// F16 = false: TF32 operands (4 B), 32 K elements per 128-byte chunk row, tcgen05 kind::tf32
+// F16 = true : FP16 operands (2 B), 64 K elements per chunk row, kind::f16 - half the bytes to gather, half the
+//              LDGSTS instructions and half the shared-memory operand traffic per K element; the 2-term split
+//              hi = fp16(x), lo = fp16(x - hi) carries the same 22 mantissa bits as the TF32 split
+template <int CI, int CO, int KV, bool CAT, bool PRECISE, bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant__ TcArgs a) {
     constexpr int KT = KV * CI;                       // GEMM K
-    constexpr int NCH = (KT + 31) / 32;               // chunks of 32 floats
+    constexpr int ES = F16 ? 2 : 4;                   // operand element size
+    constexpr int CE = 128 / ES;                      // K elements per chunk row (128 B)
+    constexpr int PE = 16 / ES;                       // K elements per 16-byte piece
+    constexpr int NCH = (KT + CE - 1) / CE;           // chunks
     constexpr int NP = CO < 16 ? 16 : CO;             // UMMA N (M=128 needs N % 16 == 0)
     constexpr int A_BYTES = 128 * 128;
     constexpr int B_BYTES = NP * 128;
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     constexpr int kTcStages = tc_stages(NP);
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t FMT = F16 ? 0u : 2u;           // a/b format: F16 = 0, TF32 = 2 (UMMA::F16F32Format)
+    constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     static_assert(CI % 8 == 0 && NP <= 64 && B_BYTES % 1024 == 0, "tile shape");
 
     extern __shared__ uint8_t smem_raw[];
@@ -189,7 +207,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
         // Lane l of a warp copies piece (l & 7) of tile rows (l >> 3) + 4m, m = 0..7: the eight lanes of a row
         // move one contiguous 128 B (or 2 x 64 B) span.  Rulebook entries are loaded by the lane that owns the
         // row, RI-1 chunks ahead (the only register loads left), and travel by shuffle.
-        constexpr int KPC = (CI >= 32) ? 1 : 32 / CI;    // kernel offsets covered by one chunk
+        constexpr int KPC = (CI >= CE) ? 1 : CE / CI;    // kernel offsets covered by one chunk
         constexpr int RI = 8;
         const int lane = tp & 31;
         const int piece = lane & 7;
@@ -202,7 +220,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
             const int row = tile * 128 + tp;
             #pragma unroll
             for (int q = 0; q < KPC; ++q) {
-                const int k = (j * 32) / CI + q;
+                const int k = (j * CE) / CI + q;
                 int n = -1;
                 if (row < a.n_out && k < KV) n = a.nbr ? __ldg(a.nbr + (size_t)k * a.n_out + row) : row;
                 nb[q] = n;
@@ -222,7 +240,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
                     const uint32_t sA_hi = smem_base + stage * STAGE_BYTES;
                     const uint32_t sA_lo = sA_hi + A_BYTES;
                     const uint32_t sB = sA_lo + A_BYTES;
-                    const int idx = j * 32 + piece * 4;
+                    const int idx = j * CE + piece * PE;
                     const int ci = idx % CI;
                     mbar_wait(empty0 + 8 * stage, ph ^ 1u);
                     #pragma unroll
@@ -232,7 +250,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
                         #pragma unroll
                         for (int q = 0; q < KPC; ++q) {
                             const int nq = __shfl_sync(0xFFFFFFFFu, ibuf[u][q], rl);
-                            if (KPC == 1 || (piece * 4) / CI == q) n = nq;
+                            if (KPC == 1 || (piece * PE) / CI == q) n = nq;
                         }
                         const bool on = (n >= 0) && (idx < KT);
                         const size_t nn = on ? (size_t)n : 0;
@@ -243,8 +261,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
                         const uint32_t rt = (uint32_t)(tp & ~31) + (uint32_t)rl;
                         const uint32_t off = rt * 128u + (uint32_t)((piece ^ (int)(rt & 7u)) << 4);
                         const uint32_t sz = on ? 16u : 0u;
-                        cp_async16(sA_hi + off, (second ? a.inB : a.inA) + eoff, sz);
-                        if (PRECISE) cp_async16(sA_lo + off, (second ? a.inB_lo : a.inA_lo) + eoff, sz);
+                        // element offsets are in operand elements (float or __half)
+                        cp_async16(sA_hi + off, (const char*)(second ? a.inB : a.inA) + eoff * ES, sz);
+                        if (PRECISE) cp_async16(sA_lo + off, (const char*)(second ? a.inB_lo : a.inA_lo) + eoff * ES, sz);
                     }
                     {   // weight chunk: hi tile then lo tile, already swizzled images (L2 resident)
                         const float* src = a.wimg + (size_t)j * (2 * B_BYTES / 4);
@@ -310,11 +329,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
                 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {        // 4 K steps of 8 tf32 (32 B) inside the 128 B swizzle span
                     const uint64_t ah = make_desc_sw128(sA_hi + ks * 32), bh = make_desc_sw128(sB_hi + ks * 32);
-                    umma_tf32(tmem_d, ah, bh, IDESC, (j | ks) ? 1u : 0u);
+                    if (F16) umma_f16(tmem_d, ah, bh, IDESC, (j | ks) ? 1u : 0u);
+                    else umma_tf32(tmem_d, ah, bh, IDESC, (j | ks) ? 1u : 0u);
                     if (PRECISE) {
                         const uint64_t al = make_desc_sw128(sA_lo + ks * 32), bl = make_desc_sw128(sB_lo + ks * 32);
-                        umma_tf32(tmem_d, al, bh, IDESC, 1u);
-                        umma_tf32(tmem_d, ah, bl, IDESC, 1u);
+                        if (F16) { umma_f16(tmem_d, al, bh, IDESC, 1u); umma_f16(tmem_d, ah, bl, IDESC, 1u); }
+                        else { umma_tf32(tmem_d, al, bh, IDESC, 1u); umma_tf32(tmem_d, ah, bl, IDESC, 1u); }
                     }
                 }
                 umma_commit(empty0 + 8 * stage);       // stage reusable once these MMAs have read it
@@ -347,6 +367,40 @@ __global__ void __launch_bounds__(256) k_act_split(const float4* __restrict__ in
     float4 h = make_float4(tf32_rn(x.x), tf32_rn(x.y), tf32_rn(x.z), tf32_rn(x.w));
     hi[i] = h;
     if (lo) lo[i] = make_float4(tf32_rn(x.x - h.x), tf32_rn(x.y - h.y), tf32_rn(x.z - h.z), tf32_rn(x.w - h.w));
+}
+
+// FP16 variant of the split: hi = fp16(x), lo = fp16(x - hi).  |x| must stay inside the FP16 range; a value above
+// 3e4 raises the flag that the engine turns into an error (measured activations of the checkpoints: <= ~1e3).
+__global__ void __launch_bounds__(256) k_act_split_f16(const float4* __restrict__ in, const float* __restrict__ bn, int c, int bn_off,
+                                                       int bn_stride, int64_t n4, uint2* __restrict__ hi, uint2* __restrict__ lo,
+                                                       int* __restrict__ range_flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 x = in[i];
+    if (bn) {
+        const int ch = (int)((i * 4) % c) + bn_off;
+        x.x = fmaxf(fmaf(x.x, bn[ch + 0], bn[bn_stride + ch + 0]), 0.f);
+        x.y = fmaxf(fmaf(x.y, bn[ch + 1], bn[bn_stride + ch + 1]), 0.f);
+        x.z = fmaxf(fmaf(x.z, bn[ch + 2], bn[bn_stride + ch + 2]), 0.f);
+        x.w = fmaxf(fmaf(x.w, bn[ch + 3], bn[bn_stride + ch + 3]), 0.f);
+    }
+    if (!(fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))) < 3.0e4f)) *range_flag = 1;
+    const __half2 h01 = __floats2half2_rn(x.x, x.y), h23 = __floats2half2_rn(x.z, x.w);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    hi[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    if (lo) {
+        const __half2 l01 = __floats2half2_rn(x.x - f01.x, x.y - f01.y), l23 = __floats2half2_rn(x.z - f23.x, x.w - f23.y);
+        lo[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+    }
+}
+
+void act_split_f16(Ctx& cx, const float* in, const float* bn, int c, int bn_off, int bn_stride, int64_t n, void* hi, void* lo,
+                   int* range_flag) {
+    int64_t n4 = n * c / 4;
+    if (n4 <= 0) return;
+    k_act_split_f16<<<div_up(n4, 256), 256, 0, cx.st>>>((const float4*)in, bn, c, bn_off, bn_stride, n4, (uint2*)hi, (uint2*)lo,
+                                                        range_flag);
+    cx.launches++;
 }
 
 void act_split(Ctx& cx, const float* in, const float* bn, int c, int bn_off, int bn_stride, int64_t n, float* hi, float* lo) {
@@ -388,20 +442,47 @@ std::vector<float> make_tc_weight_image(const float* w_kcico, int kv, int ci, in
     return img;
 }
 
+// FP16 weight image: per chunk of 64 K indices a [NP][64] K-major tile of __half, SWIZZLE_128B, hi then lo.
+// Returned as floats (two halves per float) so that it can live in the same weight blob.
+std::vector<float> make_tc_weight_image_f16(const float* w_kcico, int kv, int ci, int co) {
+    const int KT = kv * ci, NCH = (KT + 63) / 64, NP = co < 16 ? 16 : co;
+    std::vector<__half> img((size_t)NCH * 2 * NP * 64, __float2half(0.0f));
+    for (int j = 0; j < NCH; ++j)
+        for (int n = 0; n < NP; ++n)
+            for (int kk = 0; kk < 64; ++kk) {
+                int idx = j * 64 + kk;
+                float val = 0.0f;
+                if (idx < KT && n < co) val = w_kcico[(size_t)idx * co + n];
+                __half hi = __float2half_rn(val);
+                __half lo = __float2half_rn(val - __half2float(hi));
+                int p = kk / 8, e = kk % 8;
+                size_t off = (size_t)n * 64 + (size_t)((p ^ (n & 7)) * 8) + e;
+                img[(size_t)j * 2 * NP * 64 + off] = hi;
+                img[(size_t)j * 2 * NP * 64 + (size_t)NP * 64 + off] = lo;
+            }
+    std::vector<float> out((img.size() + 1) / 2, 0.0f);
+    std::memcpy(out.data(), img.data(), img.size() * sizeof(__half));
+    return out;
+}
+
 template <int CI, int CO, int KV, bool CAT>
-static void launch_tc(Ctx& cx, const TcArgs& a0, bool precise) {
+static void launch_tc(Ctx& cx, const TcArgs& a0, bool precise, bool f16) {
     TcArgs a = a0;
     if (a.n_out <= 0) return;
     a.n_tiles = div_up(a.n_out, 128);
     constexpr int NP = CO < 16 ? 16 : CO;
     constexpr size_t smem = (size_t)tc_stages(NP) * (2 * 128 * 128 + 2 * NP * 128) + 1024;
     int grid = std::min(a.n_tiles, kNumSMs);
-    if (precise) {
-        auto kern = k_conv_tc<CI, CO, KV, CAT, true>;
+    if (f16) {
+        auto kern = k_conv_tc<CI, CO, KV, CAT, true, true>;
+        SQSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kTcThreads, smem, cx.st>>>(a);
+    } else if (precise) {
+        auto kern = k_conv_tc<CI, CO, KV, CAT, true, false>;
         SQSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, kTcThreads, smem, cx.st>>>(a);
     } else {
-        auto kern = k_conv_tc<CI, CO, KV, CAT, false>;
+        auto kern = k_conv_tc<CI, CO, KV, CAT, false, false>;
         SQSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, kTcThreads, smem, cx.st>>>(a);
     }
@@ -411,13 +492,13 @@ static void launch_tc(Ctx& cx, const TcArgs& a0, bool precise) {
 // Dispatch on the shapes that occur in SmartTreeXX. Returns false for shapes it does not cover.
 bool conv_tc(Ctx& cx, int ci, int co, int kv, bool cat, const float* inA, const float* inB, const float* inA_lo,
              const float* inB_lo, const int32_t* nbr, const float* wimg, const float* res, const float* sel_src,
-             const uint8_t* sel_flag, float* out, int64_t n_out, bool precise) {
+             const uint8_t* sel_flag, float* out, int64_t n_out, bool precise, bool f16) {
     TcArgs a;
     a.inA = inA; a.inB = inB; a.inA_lo = inA_lo; a.inB_lo = inB_lo; a.nbr = nbr; a.wimg = wimg; a.res = res; a.sel_src = sel_src; a.sel_flag = sel_flag;
     a.out = out; a.n_out = (int)n_out; a.n_tiles = 0;
 #define SQSM_TC_CASE(CI_, CO_, KV_, CAT_)                                         \
     if (ci == CI_ && co == CO_ && kv == KV_ && cat == CAT_) {                     \
-        launch_tc<CI_, CO_, KV_, CAT_>(cx, a, precise);                           \
+        launch_tc<CI_, CO_, KV_, CAT_>(cx, a, precise, f16);                      \
         return true;                                                              \
     }
     SQSM_TC_CASE(16, 16, 27, false) SQSM_TC_CASE(32, 32, 27, false) SQSM_TC_CASE(64, 64, 27, false)

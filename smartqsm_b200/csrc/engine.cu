@@ -125,9 +125,9 @@ extern "C" int sqsm_finalize_weights(sqsm_handle h) {
     SQSM_API_BEGIN(h)
     net_upload(h->cx, h->nw, h->state, h->cfg.down_kernel_flip != 0);
     int mode = h->cfg.conv_mode;
-    if (mode == 0) { const char* env = getenv("SQSM_CONV_MODE"); mode = env ? atoi(env) : 2; }
-    SQSM_CHECK(mode >= 1 && mode <= 3, "conv_mode must be 0..3");
-    h->nw.mode = mode - 1;                                   // 0 FFMA, 1 3xTF32, 2 TF32
+    if (mode == 0) { const char* env = getenv("SQSM_CONV_MODE"); mode = env ? atoi(env) : 4; }
+    SQSM_CHECK(mode >= 1 && mode <= 4, "conv_mode must be 0..4");
+    h->nw.mode = mode - 1;                                   // 0 FFMA, 1 3xTF32, 2 TF32, 3 3xFP16
     if (const char* env = getenv("SQSM_TC_MIN_CO")) h->nw.tc_min_co = atoi(env);
     SQSM_API_END(h)
 }
@@ -328,6 +328,12 @@ extern "C" int sqsm_contract_step(sqsm_handle h, SqsmIterStats* stats) {
             d.valid = true;
         }
         s0 = s1;
+    }
+    if (h->nw.mode == 3) {
+        int flag = 0;
+        SQSM_CUDA(cudaMemcpyAsync(&flag, h->nw.range_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SQSM_CUDA(cudaStreamSynchronize(st));
+        SQSM_CHECK(flag == 0, "an activation exceeded the FP16 range in conv_mode 4 (3xFP16); use conv_mode 2 (3xTF32)");
     }
     s.n_out = out_base;
     if (Trace::enabled()) fprintf(stderr, "[trace] ---- end of passes, n_out %lld\n", (long long)out_base);

@@ -53,7 +53,8 @@ struct ConvW {                          // one convolution, device resident
     int ci = 0, co = 0, kv = 0;
     float* w = nullptr;                 // [kv][ci][co]
     float* bn = nullptr;                // [2][ci] alpha, beta of the BatchNorm+ReLU in FRONT of the conv (or null)
-    float* wimg = nullptr;              // tensor-core weight image (conv_tc.cu) or null
+    float* wimg = nullptr;              // tensor-core weight image, TF32 hi/lo (conv_tc.cu) or null
+    float* wimg16 = nullptr;            // tensor-core weight image, FP16 hi/lo
 };
 
 struct HeadW {                          // output_layer BN + both MLP heads; index 0 = offset, 1 = regression
@@ -68,9 +69,12 @@ struct NetWeights {
     DBuf<float> blob;
     HeadW head;
     bool ready = false;
-    int mode = 1;                       // 0 = fp32 FFMA everywhere, 1 = tcgen05 3xTF32 (fp32-class), 2 = tcgen05 single-pass TF32
-    int tc_min_co = 32;                 // layers with at least this many output channels use the tensor-core kernel
-                                        // (measured: at C=16 the FFMA kernel is faster than the gather-bound tcgen05 one)
+    int mode = 3;                       // 0 = fp32 FFMA everywhere, 1 = tcgen05 3xTF32 (fp32-class), 2 = tcgen05 single-pass TF32,
+                                        // 3 = tcgen05 3xFP16 (2-term FP16 split, fp32-class, half the operand bytes)
+    int* range_flag = nullptr;          // device flag: an activation left the FP16 range in mode 3
+    int tc_min_co = 16;                 // layers with at least this many output channels use the tensor-core kernel
+                                        // (measured: with FP16 operands the tcgen05 kernel wins from C=16 up; with TF32
+                                        // operands only from C=32)
 };
 
 struct Net;                             // conv.cu
