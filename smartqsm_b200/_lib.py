@@ -217,6 +217,19 @@ class Engine:
             self._check(self._lib.sqsm_radius_graph(self._h, r, C.byref(e), _ptr(out)), "radius_graph")
         return out
 
+    def skeletal_sample_into(self, voxel: float, ids_ptr: int, pts_ptr: int, rad_ptr: int) -> int:
+        """Copy the skeletal sample into caller-provided host buffers (e.g. pinned memory); returns M."""
+        m = C.c_int64()
+        self._check(self._lib.sqsm_skeletal_sample(self._h, voxel, C.byref(m), C.c_void_p(ids_ptr), C.c_void_p(pts_ptr),
+                                                   C.c_void_p(rad_ptr)), "skeletal_sample")
+        return m.value
+
+    def radius_graph_into(self, r: float, edges_ptr: int) -> int:
+        """Copy the edge list into a caller-provided host buffer of at least 16 * E bytes; returns E."""
+        e = C.c_int64()
+        self._check(self._lib.sqsm_radius_graph(self._h, r, C.byref(e), C.c_void_p(edges_ptr)), "radius_graph")
+        return e.value
+
     def radius_graph_points(self, pts: np.ndarray, r: float) -> np.ndarray:
         a = np.ascontiguousarray(pts, dtype=np.float32)
         e = C.c_int64()

@@ -144,50 +144,81 @@ __global__ void __launch_bounds__(256) k_conv(ConvArgs a) {
 
 // SparseInverseConv3d(k=2): every fine row has exactly one (parent, kernel offset) pair, so
 // out[i] = W[koff[i]] . bnrelu(in_c[parent[i]]) (zeros when the voxel did not survive the down-sample).
-// Thread = one row x 8 output channels; the 8 weight matrices sit in shared memory.
+// A block takes a tile of 1024 rows, buckets them by kernel offset into 8 shared-memory lists and then runs 8
+// dense passes: inside a pass every lane uses the SAME weight matrix, so the weights are warp-broadcast
+// shared-memory reads (a per-lane offset makes them 8-way conflicting and the kernel shared-memory bound).
 template <int CI, int CO>
 __global__ void __launch_bounds__(256) k_upconv(const float* __restrict__ in, const int32_t* __restrict__ parent,
                                                 const int32_t* __restrict__ koff, const float* __restrict__ w,
                                                 const float* __restrict__ bn, float* __restrict__ out, int n) {
-    constexpr int SL = CO / 8;                       // channel slices per row
+    constexpr int T = 1024;
     extern __shared__ __align__(16) float smem[];
     float* sbn = smem;                               // [2][CI]
-    float* sw = smem + 2 * CI;                       // [8][CI*CO + 8]: 32 B of padding per offset so that lanes holding
-                                                     // different kernel offsets read different shared-memory banks
-    constexpr int KS = CI * CO + 8;
-    for (int i = threadIdx.x; i < 2 * CI; i += 256) sbn[i] = bn[i];
-    for (int i = threadIdx.x; i < 8 * CI * CO / 4; i += 256) {
-        const int k = i / (CI * CO / 4), r = i % (CI * CO / 4);
-        reinterpret_cast<float4*>(sw + (size_t)k * KS)[r] = reinterpret_cast<const float4*>(w)[i];
-    }
+    float* sw = smem + 2 * CI;                       // [CI][CO] weights of the current offset
+    uint16_t* lists = reinterpret_cast<uint16_t*>(sw + CI * CO);   // [8][T] local rows per kernel offset
+    __shared__ int cnt[8];
+    const int t = threadIdx.x, lane = t & 31;
+    const int tile0 = blockIdx.x * T;
+    for (int i = t; i < 2 * CI; i += 256) sbn[i] = bn[i];
+    if (t < 8) cnt[t] = 0;
     __syncthreads();
-    // persistent blocks: the 8 weight matrices are staged once per block, not once per 256 rows
-    const int64_t total = (int64_t)n * SL;
-    for (int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x; g < total; g += (int64_t)gridDim.x * 256) {
-    const int row = (int)(g / SL), sl = (int)(g % SL);
-    const int p = parent[row];
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (p >= 0) {
-        const float* wk = sw + (size_t)koff[row] * KS + sl * 8;
-        const float4* src = reinterpret_cast<const float4*>(in + (size_t)p * CI);
-        #pragma unroll
-        for (int c0 = 0; c0 < CI; c0 += 4) {
-            float4 x = __ldg(src + c0 / 4);
-            float v[4] = {x.x, x.y, x.z, x.w};
-            #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                const float a = fmaxf(fmaf(v[cc], sbn[c0 + cc], sbn[CI + c0 + cc]), 0.0f);
-                const float4 w0 = *reinterpret_cast<const float4*>(wk + (size_t)(c0 + cc) * CO);
-                const float4 w1 = *reinterpret_cast<const float4*>(wk + (size_t)(c0 + cc) * CO + 4);
-                acc[0] = fmaf(a, w0.x, acc[0]); acc[1] = fmaf(a, w0.y, acc[1]); acc[2] = fmaf(a, w0.z, acc[2]);
-                acc[3] = fmaf(a, w0.w, acc[3]); acc[4] = fmaf(a, w1.x, acc[4]); acc[5] = fmaf(a, w1.y, acc[5]);
-                acc[6] = fmaf(a, w1.z, acc[6]); acc[7] = fmaf(a, w1.w, acc[7]);
+    // bucket the tile's rows by kernel offset (one shared-memory atomic per warp and offset)
+    #pragma unroll
+    for (int j = 0; j < T / 256; ++j) {
+        const int lr = j * 256 + t, row = tile0 + lr;
+        int k = -1;
+        if (row < n) {
+            if (parent[row] >= 0) k = koff[row];
+            else {
+                float4* dst = reinterpret_cast<float4*>(out + (size_t)row * CO);
+                #pragma unroll
+                for (int c = 0; c < CO / 4; ++c) dst[c] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
+        #pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, k == kk);
+            if (m == 0) continue;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&cnt[kk], __popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (k == kk) lists[kk * T + base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)lr;
+        }
     }
-    float4* dst = reinterpret_cast<float4*>(out + (size_t)row * CO + sl * 8);
-    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    for (int kk = 0; kk < 8; ++kk) {
+        __syncthreads();                             // lists complete / previous weights consumed
+        for (int i = t; i < CI * CO / 4; i += 256)
+            reinterpret_cast<float4*>(sw)[i] = reinterpret_cast<const float4*>(w + (size_t)kk * CI * CO)[i];
+        __syncthreads();
+        const int P = cnt[kk];
+        for (int i = t; i < P; i += 256) {
+            const int row = tile0 + (int)lists[kk * T + i];
+            const float4* src = reinterpret_cast<const float4*>(in + (size_t)parent[row] * CI);
+            float acc[CO];
+            #pragma unroll
+            for (int c = 0; c < CO; ++c) acc[c] = 0.0f;
+            #pragma unroll
+            for (int c0 = 0; c0 < CI; c0 += 4) {
+                const float4 x = __ldg(src + c0 / 4);
+                const float v[4] = {x.x, x.y, x.z, x.w};
+                #pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const float av = fmaxf(fmaf(v[cc], sbn[c0 + cc], sbn[CI + c0 + cc]), 0.0f);
+                    const float* wrow = sw + (c0 + cc) * CO;
+                    #pragma unroll
+                    for (int q = 0; q < CO / 4; ++q) {
+                        const float4 wv = *reinterpret_cast<const float4*>(wrow + 4 * q);
+                        acc[4 * q + 0] = fmaf(av, wv.x, acc[4 * q + 0]);
+                        acc[4 * q + 1] = fmaf(av, wv.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(av, wv.z, acc[4 * q + 2]);
+                        acc[4 * q + 3] = fmaf(av, wv.w, acc[4 * q + 3]);
+                    }
+                }
+            }
+            float4* dst = reinterpret_cast<float4*>(out + (size_t)row * CO);
+            #pragma unroll
+            for (int c = 0; c < CO / 4; ++c) dst[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+        }
     }
 }
 
@@ -195,12 +226,10 @@ template <int CI, int CO>
 static void launch_upconv(Ctx& cx, const ConvW& w, const float* in, const int32_t* parent, const int32_t* koff, float* out,
                           int64_t n) {
     if (n <= 0) return;
-    const size_t smem = (size_t)(2 * CI + 8 * (CI * CO + 8)) * 4;
+    const size_t smem = (size_t)(2 * CI + CI * CO) * 4 + (size_t)8 * 1024 * sizeof(uint16_t);
     auto kern = k_upconv<CI, CO>;
     if (smem > 48 * 1024) SQSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int per_sm = smem > 48 * 1024 ? 2 : 6;
-    const int grid = std::min<int64_t>(div_up(n * (CO / 8), 256), (int64_t)kNumSMs * per_sm);
-    kern<<<grid, 256, smem, cx.st>>>(in, parent, koff, w.w, w.bn, out, (int)n);
+    kern<<<div_up(n, 1024), 256, smem, cx.st>>>(in, parent, koff, w.w, w.bn, out, (int)n);
     cx.launches++;
 }
 

@@ -501,6 +501,7 @@ bool conv_tc(Ctx& cx, int ci, int co, int kv, bool cat, const float* inA, const 
         launch_tc<CI_, CO_, KV_, CAT_>(cx, a, precise, f16);                      \
         return true;                                                              \
     }
+    SQSM_TC_CASE(8, 8, 27, false) SQSM_TC_CASE(16, 8, 27, true) SQSM_TC_CASE(16, 8, 1, true)
     SQSM_TC_CASE(16, 16, 27, false) SQSM_TC_CASE(32, 32, 27, false) SQSM_TC_CASE(64, 64, 27, false)
     SQSM_TC_CASE(32, 16, 27, true) SQSM_TC_CASE(64, 32, 27, true)
     SQSM_TC_CASE(32, 16, 1, true) SQSM_TC_CASE(64, 32, 1, true)
