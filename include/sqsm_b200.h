@@ -94,6 +94,23 @@ int  sqsm_set_state_f32(sqsm_handle h, const float* h_xyz, const float* h_disp, 
  * (spconv_based_contraction.py:75-140).  `stats` may be NULL. */
 int  sqsm_contract_step(sqsm_handle h, SqsmIterStats* stats);
 
+/* The same thunk in phases, for ONE tree sharded over several ranks.  Cube batches are
+ * independent inside an iteration (synthetic_tree.py:252-281), so rank `shard` of `n_shards` runs voxelisation,
+ * rulebooks and the U-Net for a contiguous range of batches only and yields a SEGMENT of the new cloud; the
+ * concatenation of the segments in rank order is the new cloud in canonical order (identical to the
+ * single-rank result).  The caller exchanges the segments (NCCL), installs the assembled cloud on every rank,
+ * all-reduces the partial Chamfer sums and finishes with the same decision everywhere.
+ *   sqsm_step_begin(h, r, R, stats)            -> stats.n_out = rows of this rank's segment
+ *   sqsm_step_segment(h, &n, d_xyz, d_disp)    -> copy the segment to DEVICE buffers (NULL: size only)
+ *   sqsm_step_set_candidate(h, d_xyz, d_disp, n)   assembled new cloud, DEVICE pointers
+ *   sqsm_step_chamfer(h, r, R, sums[2], counts[2]) partial sums over query bricks b = r (mod R)
+ *   sqsm_step_finish(h, monitored, chamfer, &accepted)   accept / reject like :123-131 */
+int  sqsm_step_begin(sqsm_handle h, int32_t shard, int32_t n_shards, SqsmIterStats* stats);
+int  sqsm_step_segment(sqsm_handle h, int64_t* n, float* d_dst_xyz, float* d_dst_disp);
+int  sqsm_step_set_candidate(sqsm_handle h, const float* d_xyz, const float* d_disp, int64_t n);
+int  sqsm_step_chamfer(sqsm_handle h, int32_t shard, int32_t n_shards, double* sums2, int64_t* counts2);
+int  sqsm_step_finish(sqsm_handle h, int32_t monitored, double chamfer, int32_t* accepted);
+
 /* SpconvBasedContraction.output() (spconv_based_contraction.py:147-151): sizes, then copy. */
 int  sqsm_result_size(sqsm_handle h, int64_t* n);
 int  sqsm_get_result(sqsm_handle h, float* h_contracted_xyz, float* h_displacements_xyz);

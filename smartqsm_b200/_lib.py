@@ -43,6 +43,7 @@ class SqsmIterStats(C.Structure):
 EXPORTS = [
     "sqsm_create", "sqsm_destroy", "sqsm_last_error", "sqsm_abi_version", "sqsm_set_weight",
     "sqsm_finalize_weights", "sqsm_set_points_f64", "sqsm_set_points_dev_f32", "sqsm_set_state_f32", "sqsm_contract_step",
+    "sqsm_step_begin", "sqsm_step_segment", "sqsm_step_set_candidate", "sqsm_step_chamfer", "sqsm_step_finish",
     "sqsm_result_size", "sqsm_get_result", "sqsm_skeletal_sample", "sqsm_radius_graph",
     "sqsm_radius_graph_points", "sqsm_debug_capture", "sqsm_debug_level_size", "sqsm_debug_voxels",
     "sqsm_debug_batch_shapes", "sqsm_debug_level_tables", "sqsm_debug_canon_to_internal",
@@ -76,6 +77,11 @@ def load_library() -> C.CDLL:
         "sqsm_set_points_dev_f32": ([vp, vp, i64], C.c_int),
         "sqsm_set_state_f32": ([vp, vp, vp, i64], C.c_int),
         "sqsm_contract_step": ([vp, P(SqsmIterStats)], C.c_int),
+        "sqsm_step_begin": ([vp, i32, i32, P(SqsmIterStats)], C.c_int),
+        "sqsm_step_segment": ([vp, P(i64), vp, vp], C.c_int),
+        "sqsm_step_set_candidate": ([vp, vp, vp, i64], C.c_int),
+        "sqsm_step_chamfer": ([vp, i32, i32, P(f64), P(i64)], C.c_int),
+        "sqsm_step_finish": ([vp, i32, f64, P(i32)], C.c_int),
         "sqsm_result_size": ([vp, P(i64)], C.c_int),
         "sqsm_get_result": ([vp, vp, vp], C.c_int),
         "sqsm_skeletal_sample": ([vp, f64, P(i64), vp, vp, vp], C.c_int),
@@ -173,6 +179,32 @@ class Engine:
         st = SqsmIterStats()
         self._check(self._lib.sqsm_contract_step(self._h, C.byref(st)), "contract_step")
         return st.as_dict()
+
+    # ---- phased thunk (one tree sharded over several ranks; device pointers are raw ints)
+    def step_begin(self, shard: int, n_shards: int) -> dict:
+        st = SqsmIterStats()
+        self._check(self._lib.sqsm_step_begin(self._h, shard, n_shards, C.byref(st)), "step_begin")
+        return st.as_dict()
+
+    def step_segment(self, d_xyz: int = 0, d_disp: int = 0) -> int:
+        n = C.c_int64()
+        self._check(self._lib.sqsm_step_segment(self._h, C.byref(n), C.c_void_p(d_xyz or None), C.c_void_p(d_disp or None)),
+                    "step_segment")
+        return n.value
+
+    def step_set_candidate(self, d_xyz: int, d_disp: int, n: int) -> None:
+        self._check(self._lib.sqsm_step_set_candidate(self._h, C.c_void_p(d_xyz), C.c_void_p(d_disp), n), "step_set_candidate")
+
+    def step_chamfer(self, shard: int, n_shards: int):
+        sums = (C.c_double * 2)()
+        counts = (C.c_int64 * 2)()
+        self._check(self._lib.sqsm_step_chamfer(self._h, shard, n_shards, sums, counts), "step_chamfer")
+        return [sums[0], sums[1]], [counts[0], counts[1]]
+
+    def step_finish(self, monitored: bool, chamfer: float) -> bool:
+        acc = C.c_int32()
+        self._check(self._lib.sqsm_step_finish(self._h, int(monitored), float(chamfer), C.byref(acc)), "step_finish")
+        return bool(acc.value)
 
     def result(self) -> Tuple[np.ndarray, np.ndarray]:
         n = C.c_int64()

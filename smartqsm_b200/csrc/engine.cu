@@ -31,6 +31,10 @@ struct sqsm_engine {
     NetWeights nw;
     DBuf<float> P, D;
     int64_t n = 0;
+    DBuf<float> candP, candD;       // candidate state of the running thunk (this rank's segment, or the assembled cloud)
+    int64_t cand_n = 0;
+    bool cand_valid = false;
+    int64_t step_launches0 = 0;
     int epoch = 0;
     double chamfer_prev = std::numeric_limits<double>::infinity();
     bool early_stopped = false;
@@ -222,29 +226,53 @@ struct StageTimer {
     float between(int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, ev[a], ev[b]); return ms; }
 };
 
-extern "C" int sqsm_contract_step(sqsm_handle h, SqsmIterStats* stats) {
-    SQSM_API_BEGIN(h)
+// ---- one _contract() thunk in three phases (so that a single tree can be sharded over several ranks) --------------
+//
+//   begin   : tiling of the whole cloud, then voxelisation -> rulebooks -> U-Net -> decode for the cube batches of this
+//             shard (contiguous batch range, balanced by entry count); result = a SEGMENT of the new cloud
+//   (ranks exchange their segments; the concatenation in rank order is the new cloud in canonical order)
+//   chamfer : partial sums of the monitor over this shard's query bricks (all-reduced by the caller)
+//   finish  : accept (state <- candidate) or reject
+// sqsm_contract_step() is begin(0,1) + chamfer(0,1) + finish on one rank.
+
+static void shard_batch_range(const TilingResult& tl, int batch_size, int shard, int n_shards, int* s_lo, int* s_hi) {
+    // contiguous batch ranges with about E / n_shards entries each; identical on every rank
+    const int nb = tl.n_batches;
+    const int64_t E = tl.n_entries;
+    auto batch_start_entry = [&](int b) { return tl.start[std::min(b * batch_size, tl.n_samples)]; };
+    auto first_batch_at = [&](int64_t target) {
+        int lo = 0, hi = nb;
+        while (lo < hi) { int mid = (lo + hi) / 2; if (batch_start_entry(mid) < target) lo = mid + 1; else hi = mid; }
+        return lo;
+    };
+    int b0 = (shard == 0) ? 0 : first_batch_at(E * shard / n_shards);
+    int b1 = (shard == n_shards - 1) ? nb : first_batch_at(E * (shard + 1) / n_shards);
+    *s_lo = std::min(b0 * batch_size, tl.n_samples);
+    *s_hi = std::min(b1 * batch_size, tl.n_samples);
+}
+
+static void step_begin(sqsm_engine* h, int shard, int n_shards, SqsmIterStats& s) {
     SQSM_CHECK(h->n > 0, "no points set");
     SQSM_CHECK(h->nw.ready, "weights not finalised");
+    SQSM_CHECK(n_shards >= 1 && shard >= 0 && shard < n_shards, "bad shard index");
     Ctx& cx = h->cx;
     cudaStream_t st = cx.st;
     const SqsmConfig& cfg = h->cfg;
-    SqsmIterStats s;
     std::memset(&s, 0, sizeof(s));
     s.chamfer = std::numeric_limits<double>::quiet_NaN();
     h->epoch += 1;                                                          // :76
     s.epoch = h->epoch;
     s.n_in = h->n;
-    const int64_t launches0 = cx.launches;
+    h->cand_valid = false;
+    h->step_launches0 = cx.launches;
     if (h->early_stopped) {                                                 // :77-80
         s.skipped = 1;
-        if (stats) *stats = s;
-        return 0;
+        return;
     }
     h->sk_valid = false;
     h->edges_r = -1.0;
     h->dbg.valid = false;
-    float ms_tile = 0, ms_vox = 0, ms_rule = 0, ms_net = 0, ms_cd = 0;
+    float ms_vox = 0, ms_rule = 0, ms_net = 0;
     StageTimer T0(st);
     T0.mark();
     TilingResult tl;
@@ -257,18 +285,20 @@ extern "C" int sqsm_contract_step(sqsm_handle h, SqsmIterStats* stats) {
     s.n_entries = tl.n_entries;
     s.n_cubes = tl.n_samples;
     s.n_batches = tl.n_batches;
-    DBuf<float> newP(tl.n_entries * 3, st), newD(tl.n_entries * 3, st);
+    int S0 = 0, S1 = tl.n_samples;
+    if (n_shards > 1) shard_batch_range(tl, cfg.batch_size, shard, n_shards, &S0, &S1);
+    const int64_t seg_entries = tl.start[S1] - tl.start[S0];
+    h->candP.alloc(std::max<int64_t>(seg_entries, 1) * 3, st);
+    h->candD.alloc(std::max<int64_t>(seg_entries, 1) * 3, st);
     int64_t out_base = 0;
-    int passes = 0;
-    for (int s0 = 0; s0 < tl.n_samples;) {
+    for (int s0 = S0; s0 < S1;) {
         // a pass = as many whole batches (cfg.batch_size cubes) as fit the entry budget
         int s1 = s0;
-        while (s1 < tl.n_samples) {
-            int nxt = std::min(s1 + cfg.batch_size, tl.n_samples);
+        while (s1 < S1) {
+            int nxt = std::min(s1 + cfg.batch_size, S1);
             if (s1 > s0 && tl.start[nxt] - tl.start[s0] > h->max_entries_per_pass) break;
             s1 = nxt;
         }
-        ++passes;
         const int batch0 = s0 / cfg.batch_size;
         const int nb = (s1 - 1) / cfg.batch_size - batch0 + 1;
         StageTimer T(st);
@@ -308,7 +338,7 @@ extern "C" int sqsm_contract_step(sqsm_handle h, SqsmIterStats* stats) {
         if (n_levels > 2) { s.n_rows_l2 += lv[2].n; s.pairs_l2 += lv[2].pairs; }
         if (n_levels > 3) { s.n_rows_l3 += lv[3].n; s.pairs_l3 += lv[3].pairs; }
         ForwardBuffers fb;
-        { Trace tr(cx, "net_forward"); net_forward(cx, h->nw, lv, rows, n_levels, fb, h->capture, newP.p, newD.p); }  // :100-108
+        { Trace tr(cx, "net_forward"); net_forward(cx, h->nw, lv, rows, n_levels, fb, h->capture, h->candP.p, h->candD.p); }  // :100-108
         T.mark();
         SQSM_CUDA(cudaStreamSynchronize(st));
         ms_vox += T.between(0, 1);
@@ -316,7 +346,7 @@ extern "C" int sqsm_contract_step(sqsm_handle h, SqsmIterStats* stats) {
         ms_net += T.between(2, 3);
         out_base += n_out;
         if (h->capture) {
-            SQSM_CHECK(s0 == 0 && s1 == tl.n_samples,
+            SQSM_CHECK(n_shards == 1 && s0 == 0 && s1 == tl.n_samples,
                        "debug capture needs the whole iteration in one pass (raise SQSM_MAX_ENTRIES_PER_PASS)");
             DebugCapture& d = h->dbg;
             d.n_levels = n_levels;
@@ -337,41 +367,118 @@ extern "C" int sqsm_contract_step(sqsm_handle h, SqsmIterStats* stats) {
     }
     s.n_out = out_base;
     if (Trace::enabled()) fprintf(stderr, "[trace] ---- end of passes, n_out %lld\n", (long long)out_base);
-    SQSM_CHECK(out_base > 0, "contraction produced no interior voxel");
+    SQSM_CHECK(n_shards > 1 || out_base > 0, "contraction produced no interior voxel");
+    h->cand_n = out_base;
+    h->cand_valid = true;
+    SQSM_CUDA(cudaStreamSynchronize(st));
+    s.ms_tiling = T0.between(0, 1); s.ms_voxel = ms_vox; s.ms_rulebook = ms_rule; s.ms_network = ms_net;
+    s.gpu_launches = (int32_t)(cx.launches - h->step_launches0);
+}
+
+static void step_chamfer(sqsm_engine* h, int shard, int n_shards, double sums[2], int64_t counts[2], float* ms) {
+    SQSM_CHECK(h->cand_valid && h->cand_n > 0, "no candidate state (call sqsm_step_begin / sqsm_step_set_candidate first)");
+    Ctx& cx = h->cx;
+    StageTimer T(cx.st);
+    T.mark();
+    {
+        // B_cd of SURVEY 8(d): both clouds read (12 B/point) + voxel means written and read (2 x 24 B/voxel ~ per point)
+        Trace tr(cx, "chamfer");
+        ProfScope ps(cx, "chamfer", (double)(h->n + h->cand_n) * (12.0 + 2 * 20.0), 0.0);
+        chamfer_partial(cx, h->P.p, h->n, h->candP.p, h->cand_n, (double)h->cfg.voxel_size, shard, n_shards, sums, counts);
+    }
+    T.mark();
+    SQSM_CUDA(cudaStreamSynchronize(cx.st));
+    if (ms) *ms = T.between(0, 1);
+}
+
+// accept/reject exactly like spconv_based_contraction.py:123-131
+static bool step_finish(sqsm_engine* h, bool monitored, double cd) {
+    SQSM_CHECK(h->cand_valid, "no candidate state");
     bool accept = true;
-    if (cfg.monitored_by_chamfer_distance) {                                 // :112-128
-        StageTimer T(st);
-        T.mark();
-        double cd;
-        {
-            // B_cd of SURVEY 8(d): both clouds read (12 B/point) + voxel means written and read (2 x 24 B/voxel ~ per point)
-            Trace tr(cx, "chamfer");
-            ProfScope ps(cx, "chamfer", (double)(h->n + out_base) * (12.0 + 2 * 20.0), 0.0);
-            cd = chamfer_distance(cx, h->P.p, h->n, newP.p, out_base, (double)cfg.voxel_size);
-        }
-        T.mark();
-        SQSM_CUDA(cudaStreamSynchronize(st));
-        ms_cd = T.between(0, 1);
-        s.chamfer = cd;
+    if (monitored) {
         if (cd > h->chamfer_prev) {
             accept = false;
-            if (cfg.latch_early_stop) h->early_stopped = true;
+            if (h->cfg.latch_early_stop) h->early_stopped = true;
         } else {
             h->chamfer_prev = cd;
         }
     }
     if (accept) {                                                            // :130-131
-        h->P = std::move(newP);
-        h->D = std::move(newD);
-        h->n = out_base;
+        std::swap(h->P, h->candP);
+        std::swap(h->D, h->candD);
+        h->n = h->cand_n;
     }
-    SQSM_CUDA(cudaStreamSynchronize(st));
-    ms_tile = T0.between(0, 1);
-    s.accepted = accept ? 1 : 0;
-    s.gpu_launches = (int32_t)(cx.launches - launches0);
-    s.ms_tiling = ms_tile; s.ms_voxel = ms_vox; s.ms_rulebook = ms_rule; s.ms_network = ms_net; s.ms_chamfer = ms_cd;
-    (void)passes;
+    h->cand_valid = false;
+    SQSM_CUDA(cudaStreamSynchronize(h->cx.st));
+    return accept;
+}
+
+extern "C" int sqsm_contract_step(sqsm_handle h, SqsmIterStats* stats) {
+    SQSM_API_BEGIN(h)
+    SqsmIterStats s;
+    step_begin(h, 0, 1, s);
+    if (!s.skipped) {
+        double cd = std::numeric_limits<double>::quiet_NaN();
+        if (h->cfg.monitored_by_chamfer_distance) {                          // :112-128
+            double sums[2];
+            int64_t counts[2];
+            step_chamfer(h, 0, 1, sums, counts, &s.ms_chamfer);
+            cd = sums[0] / (double)counts[0] + sums[1] / (double)counts[1];  // :122
+            s.chamfer = cd;
+        }
+        s.accepted = step_finish(h, h->cfg.monitored_by_chamfer_distance != 0, cd) ? 1 : 0;
+        s.gpu_launches = (int32_t)(h->cx.launches - h->step_launches0);
+    }
     if (stats) *stats = s;
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_step_begin(sqsm_handle h, int32_t shard, int32_t n_shards, SqsmIterStats* stats) {
+    SQSM_API_BEGIN(h)
+    SqsmIterStats s;
+    step_begin(h, shard, n_shards, s);
+    if (stats) *stats = s;
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_step_segment(sqsm_handle h, int64_t* n, float* d_dst_xyz, float* d_dst_disp) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(h->cand_valid && n, "no segment (call sqsm_step_begin first)");
+    *n = h->cand_n;
+    cudaStream_t st = h->cx.st;
+    if (d_dst_xyz && h->cand_n > 0)
+        SQSM_CUDA(cudaMemcpyAsync(d_dst_xyz, h->candP.p, sizeof(float) * 3 * h->cand_n, cudaMemcpyDeviceToDevice, st));
+    if (d_dst_disp && h->cand_n > 0)
+        SQSM_CUDA(cudaMemcpyAsync(d_dst_disp, h->candD.p, sizeof(float) * 3 * h->cand_n, cudaMemcpyDeviceToDevice, st));
+    SQSM_CUDA(cudaStreamSynchronize(st));
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_step_set_candidate(sqsm_handle h, const float* d_xyz, const float* d_disp, int64_t n) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(d_xyz && d_disp && n > 0 && n < (1ll << 31), "bad candidate arrays");
+    cudaStream_t st = h->cx.st;
+    h->candP.alloc(n * 3, st);
+    h->candD.alloc(n * 3, st);
+    SQSM_CUDA(cudaMemcpyAsync(h->candP.p, d_xyz, sizeof(float) * 3 * n, cudaMemcpyDeviceToDevice, st));
+    SQSM_CUDA(cudaMemcpyAsync(h->candD.p, d_disp, sizeof(float) * 3 * n, cudaMemcpyDeviceToDevice, st));
+    h->cand_n = n;
+    h->cand_valid = true;
+    SQSM_CUDA(cudaStreamSynchronize(st));
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_step_chamfer(sqsm_handle h, int32_t shard, int32_t n_shards, double* sums2, int64_t* counts2) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(sums2 && counts2, "null argument");
+    step_chamfer(h, shard, n_shards, sums2, counts2, nullptr);
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_step_finish(sqsm_handle h, int32_t monitored, double chamfer, int32_t* accepted) {
+    SQSM_API_BEGIN(h)
+    bool acc = step_finish(h, monitored != 0, chamfer);
+    if (accepted) *accepted = acc ? 1 : 0;
     SQSM_API_END(h)
 }
 

@@ -112,6 +112,8 @@ bool build_down(Ctx& cx, LevelTables& L, LevelTables& Lnext, int batch0, int n_b
 
 // spatial.cu
 double chamfer_distance(Ctx& cx, const float* d_P, int64_t np, const float* d_Q, int64_t nq, double voxel);
+void chamfer_partial(Ctx& cx, const float* d_P, int64_t np, const float* d_Q, int64_t nq, double voxel, int shard,
+                     int n_shards, double sums[2], int64_t counts[2]);
 struct SkeletalResult {
     DBuf<int64_t> ids;                  // [m] ascending original index
     DBuf<float> pts;                    // [m][3]

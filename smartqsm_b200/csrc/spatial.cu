@@ -202,8 +202,9 @@ __global__ void __launch_bounds__(kNNThreads) k_nn_sqdist(const Brick* __restric
                                                           const int2* __restrict__ abn, BrickHash hB,
                                                           const Brick* __restrict__ B, const double* __restrict__ meanB,
                                                           const float4* __restrict__ locB,
-                                                          const __grid_constant__ GridParams g, int max_ring,
-                                                          double* __restrict__ acc, unsigned long long* __restrict__ n_fallback) {
+                                                          const __grid_constant__ GridParams g, int max_ring, int shard,
+                                                          int n_shards, double* __restrict__ acc,
+                                                          unsigned long long* __restrict__ n_fallback) {
     __shared__ double s_red[kNNThreads / 32];
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * kNNThreads + threadIdx.x) >> 5;
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(kNNThreads) k_nn_sqdist(const Brick* __restric
     const double slack = 1e-6 * edge;                      // voxel means may sit an ulp outside their voxel
     double local_sum = 0.0;
     unsigned fb = 0;
-    for (int a = warp; a < nA; a += n_warps) {
+    for (int a = shard + n_shards * warp; a < nA; a += n_shards * n_warps) {   // bricks a = shard (mod n_shards)
         const int nq = A[a].count, qbase = A[a].base;
         const uint64_t key = A[a].key;
         const int2 mine = abn[(size_t)a * 32 + lane];
@@ -331,9 +332,14 @@ static void voxel_means(Ctx& cx, const float* d_P, int64_t n, const double mn[3]
     cx.launches += 3;
 }
 
-double chamfer_distance(Ctx& cx, const float* d_P, int64_t np, const float* d_Q, int64_t nq, double voxel) {
+// Partial Chamfer sums: the 1-NN squared distances of the voxel means of P to those of Q (sums[0]) and of Q to P
+// (sums[1]) restricted to the query bricks b = shard (mod n_shards); counts = number of voxel means of P and Q.
+// With n_shards = 1 this is the whole monitor; with several ranks the sums are all-reduced by the caller.
+void chamfer_partial(Ctx& cx, const float* d_P, int64_t np, const float* d_Q, int64_t nq, double voxel, int shard,
+                     int n_shards, double sums[2], int64_t counts[2]) {
     cudaStream_t st = cx.st;
     SQSM_CHECK(np > 0 && nq > 0, "Chamfer monitor needs two non-empty clouds");
+    SQSM_CHECK(n_shards >= 1 && shard >= 0 && shard < n_shards, "bad shard");
     double mnP[3], mxP[3], mnQ[3], mxQ[3], mn[3], mx[3];
     cloud_bounds(cx, d_P, np, mnP, mxP);
     cloud_bounds(cx, d_Q, nq, mnQ, mxQ);
@@ -360,21 +366,29 @@ double chamfer_distance(Ctx& cx, const float* d_P, int64_t np, const float* d_Q,
                                                                       B.gm.map.bricks.p, abn.p);
     k_cross_neighbours<<<div_up((int64_t)nB * 32, 256), 256, 0, st>>>(B.gm.map.bricks.p, nB, A.gm.map.view(),
                                                                       A.gm.map.bricks.p, ban.p);
-    int gA = std::min(div_up(nA, kNNThreads / 32), kNumSMs * 8), gB = std::min(div_up(nB, kNNThreads / 32), kNumSMs * 8);
+    int gA = std::max(1, std::min(div_up(div_up(nA, n_shards), kNNThreads / 32), kNumSMs * 8));
+    int gB = std::max(1, std::min(div_up(div_up(nB, n_shards), kNNThreads / 32), kNumSMs * 8));
     k_nn_sqdist<<<gA, kNNThreads, 0, st>>>(A.gm.map.bricks.p, nA, A.mean.p, abn.p, B.gm.map.view(), B.gm.map.bricks.p,
-                                           B.mean.p, B.loc.p, A.gm.g, max_ring, acc.p, nfb.p);
+                                           B.mean.p, B.loc.p, A.gm.g, max_ring, shard, n_shards, acc.p, nfb.p);
     k_nn_sqdist<<<gB, kNNThreads, 0, st>>>(B.gm.map.bricks.p, nB, B.mean.p, ban.p, A.gm.map.view(), A.gm.map.bricks.p,
-                                           A.mean.p, A.loc.p, A.gm.g, max_ring, acc.p + 1, nfb.p + 1);
+                                           A.mean.p, A.loc.p, A.gm.g, max_ring, shard, n_shards, acc.p + 1, nfb.p + 1);
     cx.launches += 4;
     if (Trace::enabled()) {
         auto f = nfb.to_host();
         fprintf(stderr, "[trace]  cd nn: ring-search fallbacks %llu of %lld, %llu of %lld\n", f[0], (long long)A.gm.map.n_rows,
                 f[1], (long long)B.gm.map.n_rows);
     }
-    double h[2];
-    SQSM_CUDA(cudaMemcpyAsync(h, acc.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    SQSM_CUDA(cudaMemcpyAsync(sums, acc.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     SQSM_CUDA(cudaStreamSynchronize(st));
-    return h[0] / (double)A.gm.map.n_rows + h[1] / (double)B.gm.map.n_rows;                                // :122
+    counts[0] = A.gm.map.n_rows;
+    counts[1] = B.gm.map.n_rows;
+}
+
+double chamfer_distance(Ctx& cx, const float* d_P, int64_t np, const float* d_Q, int64_t nq, double voxel) {
+    double sums[2];
+    int64_t counts[2];
+    chamfer_partial(cx, d_P, np, d_Q, nq, voxel, 0, 1, sums, counts);
+    return sums[0] / (double)counts[0] + sums[1] / (double)counts[1];                                      // :122
 }
 
 // ---------------------------------------------------------------------------------- skeletal sampling

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 from typing import Any, Callable, Dict, List, Optional, Sequence
 
-__all__ = ["partition_trees", "run_sharded"]
+__all__ = ["partition_trees", "run_sharded", "ShardedTreeContraction", "emulate_sharded_step"]
 
 
 def partition_trees(sizes: Sequence[int], world_size: int) -> List[List[int]]:
@@ -64,3 +64,123 @@ def run_sharded(sizes: Sequence[int], process_tree: Callable[[int], Dict[str, An
     if [s["tree"] for s in flat] != list(range(len(sizes))):
         raise RuntimeError("tree sharding lost or duplicated a tree")
     return flat
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# One oversized tree sharded over several GPUs
+# ------------------------------------------------------------------------------------------------------------------
+#
+# Within an iteration the reference's cube samples are independent (each carries its own 0.4 m halo,
+# external/SmartTreeXX/datasets/synthetic_tree.py:252-281) and are consumed 16 at a time (batch_size,
+# core/core_algorithms/spconv_based_contraction.py:92-100).  Every rank holds the whole cloud (24 B per point), does
+# the cheap tiling itself and runs voxelisation -> rulebooks -> U-Net only for a contiguous range of whole batches
+# (same batch composition as on one GPU, so integer and float outputs are identical).  The exchange step is the
+# all-gather of the moved points (24 B per point, NCCL over NVLink) plus an all-reduce of two float64 sums for the
+# Chamfer monitor, whose nearest-neighbour queries are split by brick.
+
+class ShardedTreeContraction:
+    """Drive one engine per rank through the phased thunk of ``include/sqsm_b200.h`` (sqsm_step_*).
+
+    ``engine`` is a ``smartqsm_b200._lib.Engine`` (or any object with the same ``step_*`` methods) that already
+    holds the full cloud (``set_points``) on ``device``.  Uses the default ``torch.distributed`` group (NCCL on
+    GPUs, gloo on CPU tensors in the tests).
+    """
+
+    def __init__(self, engine, rank: int, world_size: int, device, monitored: bool) -> None:
+        self.engine, self.rank, self.world, self.device, self.monitored = engine, rank, world_size, device, monitored
+        self.history: List[Dict[str, Any]] = []
+
+    def _sync(self) -> None:
+        # the engine works on its own CUDA stream: collectives issued on torch's stream must have completed
+        # before the engine reads their result (and vice versa the engine calls synchronise before returning)
+        import torch
+        if getattr(self.device, "type", "cpu") == "cuda":
+            torch.cuda.synchronize(self.device)
+
+    def contract(self) -> Dict[str, Any]:
+        """One ``_contract`` thunk over all ranks; returns this rank's stats with the global decision."""
+        import time
+        import torch
+        import torch.distributed as dist
+        eng = self.engine
+        t0 = time.perf_counter()
+        st = eng.step_begin(self.rank, self.world)
+        t1 = time.perf_counter()
+        if st["skipped"]:
+            self.history.append(st)
+            return st
+        sizes_t = torch.zeros(self.world, dtype=torch.int64, device=self.device)
+        sizes_t[self.rank] = st["n_out"]
+        if self.world > 1:
+            dist.all_reduce(sizes_t)
+        sizes = [int(x) for x in sizes_t.tolist()]
+        offs = [0]
+        for s in sizes:
+            offs.append(offs[-1] + s)
+        total = offs[-1]
+        if total == 0:
+            raise RuntimeError("contraction produced no interior voxel")
+        new_p = torch.empty((total, 3), dtype=torch.float32, device=self.device)
+        new_d = torch.empty((total, 3), dtype=torch.float32, device=self.device)
+        lo, hi = offs[self.rank], offs[self.rank + 1]
+        if hi > lo:
+            eng.step_segment(new_p[lo:hi].data_ptr(), new_d[lo:hi].data_ptr())
+        if self.world > 1:
+            for r in range(self.world):                       # the exchange: every rank's segment to everybody
+                if sizes[r]:
+                    dist.broadcast(new_p[offs[r]:offs[r + 1]], src=r)
+                    dist.broadcast(new_d[offs[r]:offs[r + 1]], src=r)
+        self._sync()
+        t2 = time.perf_counter()
+        eng.step_set_candidate(new_p.data_ptr(), new_d.data_ptr(), total)
+        cd = float("nan")
+        if self.monitored:
+            sums, counts = eng.step_chamfer(self.rank, self.world)
+            t = torch.tensor(sums, dtype=torch.float64, device=self.device)
+            if self.world > 1:
+                dist.all_reduce(t)
+            cd = float(t[0]) / counts[0] + float(t[1]) / counts[1]
+        st["accepted"] = int(eng.step_finish(self.monitored, cd))
+        t3 = time.perf_counter()
+        st["phase_s"] = {"begin": t1 - t0, "exchange": t2 - t1, "chamfer_finish": t3 - t2}
+        st["chamfer"] = cd
+        st["n_out_total"] = total
+        st["segment_sizes"] = sizes
+        self.history.append(st)
+        return st
+
+
+def emulate_sharded_step(engines, monitored: bool, device) -> Dict[str, Any]:
+    """The same exchange with all "ranks" in ONE process (several engines on one GPU): used by the single-GPU
+    parity test, because separate processes that wait on each other must not share a GPU."""
+    import torch
+    world = len(engines)
+    stats = [e.step_begin(r, world) for r, e in enumerate(engines)]
+    if stats[0]["skipped"]:
+        return stats[0]
+    sizes = [s["n_out"] for s in stats]
+    offs = [0]
+    for s in sizes:
+        offs.append(offs[-1] + s)
+    total = offs[-1]
+    new_p = torch.empty((total, 3), dtype=torch.float32, device=device)
+    new_d = torch.empty((total, 3), dtype=torch.float32, device=device)
+    for r, e in enumerate(engines):
+        if sizes[r]:
+            e.step_segment(new_p[offs[r]:offs[r + 1]].data_ptr(), new_d[offs[r]:offs[r + 1]].data_ptr())
+    for e in engines:
+        e.step_set_candidate(new_p.data_ptr(), new_d.data_ptr(), total)
+    cd = float("nan")
+    if monitored:
+        tot = [0.0, 0.0]
+        counts = None
+        for r, e in enumerate(engines):
+            s, counts = e.step_chamfer(r, world)
+            tot[0] += s[0]
+            tot[1] += s[1]
+        cd = tot[0] / counts[0] + tot[1] / counts[1]
+    acc = [e.step_finish(monitored, cd) for e in engines]
+    assert len(set(acc)) == 1
+    out = dict(stats[0])
+    out.update(accepted=int(acc[0]), chamfer=cd, n_out_total=total, segment_sizes=sizes)
+    return out

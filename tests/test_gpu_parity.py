@@ -327,3 +327,31 @@ def test_large_cloud_properties(random_state):
     assert idx0[:, 1:].min() >= 0 and idx0[:, 1:].max() < 480
     # every interior point of the input survives unless it shares a voxel: n_out <= n_in (+ face duplicates)
     assert st0["n_out"] <= st0["n_in"] + 1000
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_single_tree_sharded_equals_single_gpu(random_state, world):
+    """SURVEY 8(e) second row: one tree sharded by cube batches over `world` ranks (emulated with `world` engines on
+    this GPU, see smartqsm_b200.sharding.emulate_sharded_step) must give the bit-identical state, thunk by thunk,
+    and the same Chamfer decisions as the single-engine run."""
+    import torch
+    from smartqsm_b200.sharding import emulate_sharded_step
+    from smartqsm_b200.synthetic import make_tree
+    pts = make_tree(120000, 17)                       # ~20 cubes -> several batches at batch_size 2
+    kw = dict(batch_size=2, monitored_by_chamfer_distance=True)
+    ref = make_engine(random_state, **kw)
+    ref.set_points(pts)
+    shards = [make_engine(random_state, **kw) for _ in range(world)]
+    for e in shards:
+        e.set_points(pts)
+    for it in range(4):
+        st_ref = ref.contract_step()
+        st = emulate_sharded_step(shards, True, torch.device("cuda", 0))
+        assert sum(st["segment_sizes"]) == st_ref["n_out"]
+        assert st["accepted"] == st_ref["accepted"]
+        assert abs(st["chamfer"] - st_ref["chamfer"]) <= 1e-12 * st_ref["chamfer"]
+        P0, D0 = ref.result()
+        for e in shards:
+            P, D = e.result()
+            assert np.array_equal(P, P0) and np.array_equal(D, D0)
+    assert sum(1 for x in st["segment_sizes"] if x > 0) >= 2      # the work really was split
