@@ -183,128 +183,178 @@ __global__ void __launch_bounds__(256) k_cross_neighbours(const Brick* __restric
             if (id >= 0) r = make_int2(B[id].base, B[id].count);
         }
     }
+    const unsigned present = __ballot_sync(0xFFFFFFFFu, r.y > 0);
+    if (j == 27) r.x = (int)present;                                                 // entry 27: which of the 27 exist
     abn[(size_t)a * 32 + j] = r;
 }
 
 // Exact 1-NN squared distances from the voxel means of map A to those of map B, summed.
-// One warp per query brick.  Lanes are (query, candidate slice) pairs: a brick with nq <= 16 queries
-// gives every query S = 32 / pow2(nq) lanes that scan interleaved slices of the candidates.  Bricks of B
-// are visited centre first; a brick is skipped when, for every query of the warp, its nearest possible
-// point is not closer than the best distance found so far.  The query lies inside its brick, so after
-// the 27-neighbourhood everything else is at least one brick edge away; a query whose best distance
-// exceeds that bound keeps growing rings of bricks (hash probes) until it does not - exact 1-NN like the
-// KD-tree search of Open3D's compute_point_cloud_distance.
-constexpr int kNNThreads = 256;
-// visiting order of the 27 bricks: centre, 6 faces, 12 edges, 8 corners (nearest first -> best pruning)
-__constant__ int c_nn_order[27] = {13, 4, 10, 12, 14, 16, 22, 1, 3, 5, 7, 9, 11, 15, 17, 19, 21, 23, 25,
-                                   0, 2, 6, 8, 18, 20, 24, 26};
-__global__ void __launch_bounds__(kNNThreads) k_nn_sqdist(const Brick* __restrict__ A, int nA, const double* __restrict__ meanA,
-                                                          const int2* __restrict__ abn, BrickHash hB,
-                                                          const Brick* __restrict__ B, const double* __restrict__ meanB,
-                                                          const float4* __restrict__ locB,
-                                                          const __grid_constant__ GridParams g, int max_ring, int shard,
-                                                          int n_shards, double* __restrict__ acc,
-                                                          unsigned long long* __restrict__ n_fallback) {
-    __shared__ double s_red[kNNThreads / 32];
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * kNNThreads + threadIdx.x) >> 5;
-    const int n_warps = (gridDim.x * kNNThreads) >> 5;
+// Bricks of B are visited nearest first (own brick, faces, edges + corners); the query lies inside its brick, so after
+// the 27-neighbourhood everything else is at least one brick edge away; a query whose best distance exceeds that bound
+// keeps growing rings of bricks (hash probes) until it does not - exact 1-NN like the KD-tree search of Open3D's
+// compute_point_cloud_distance.
+// The monitor's nearest neighbours are close (median 2 cm, 99 % < 5.5 cm
+// against 8 cm bricks), so a query can prune most of the 27 bricks - but only with ITS OWN bound: a warp-wide vote
+// almost never prunes because some query of the warp sits next to every face, and a plain
+// thread-per-query loop diverges to the same union of bricks (ncu: 8 of 32 lanes active).  Here a warp owns 32
+// consecutive queries and works in three rounds - own brick, face bricks, edge+corner bricks.  In every round each lane
+// lists the bricks its query still needs (float32 lower bound against its current best) into a per-warp shared list,
+// and the (query, brick) pairs of that list are processed 8 at a time by 4-lane groups: float32 screening in
+// brick-local coordinates, float64 re-evaluation of anything that could win, shared-memory atomicMin on the owner's
+// best.  The ring fallback keeps the search exact.
+struct NNWarpShared {
+    float4 ql[32];
+    unsigned long long best[32];
+    int brick[32];
+    uint16_t list[32 * 20];
+};
+__device__ __forceinline__ float nn_gap2(int nb, const float* gm2, const float* gp2) {
+    const int dz = nb / 9 - 1, dy = (nb / 3) % 3 - 1, dx = nb % 3 - 1;
+    return ((dx == 0 ? 0.f : (dx < 0 ? gm2[0] : gp2[0])) + (dy == 0 ? 0.f : (dy < 0 ? gm2[1] : gp2[1])) +
+            (dz == 0 ? 0.f : (dz < 0 ? gm2[2] : gp2[2]))) * 0.999999f;
+}
+__global__ void __launch_bounds__(256) k_nn_sqdist_pairs(const Brick* __restrict__ A, const int32_t* __restrict__ row_brick,
+                                                         int64_t n_rows, const double* __restrict__ meanA,
+                                                         const float4* __restrict__ locA, const int2* __restrict__ abn,
+                                                         BrickHash hB, const Brick* __restrict__ B,
+                                                         const double* __restrict__ meanB, const float4* __restrict__ locB,
+                                                         const __grid_constant__ GridParams g, int max_ring, int shard,
+                                                         int n_shards, double* __restrict__ acc,
+                                                         unsigned long long* __restrict__ n_fallback) {
+    __shared__ NNWarpShared s_warp[8];
+    __shared__ double s_red[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    NNWarpShared& S = s_warp[w];
     const double edge = 8.0 * g.voxel;
-    const double slack = 1e-6 * edge;                      // voxel means may sit an ulp outside their voxel
+    const float edge_f = (float)edge;
+    const float slack = 1e-6f * edge_f;
+    constexpr unsigned kRoundMask[3] = {1u << 13,
+                                        (1u << 4) | (1u << 10) | (1u << 12) | (1u << 14) | (1u << 16) | (1u << 22),
+                                        0x07FFFFFFu & ~((1u << 13) | (1u << 4) | (1u << 10) | (1u << 12) | (1u << 14) | (1u << 16) | (1u << 22))};
     double local_sum = 0.0;
     unsigned fb = 0;
-    for (int a = shard + n_shards * warp; a < nA; a += n_shards * n_warps) {   // bricks a = shard (mod n_shards)
-        const int nq = A[a].count, qbase = A[a].base;
-        const uint64_t key = A[a].key;
-        const int2 mine = abn[(size_t)a * 32 + lane];
-        const unsigned present = __ballot_sync(0xFFFFFFFFu, lane < 27 && mine.y > 0);
-        const int bz = (int)key_z(key), by = (int)key_y(key), bx = (int)key_x(key);
-        int S = 1;                                          // lanes per query
-        if (nq <= 16) { int p2 = 1; while (p2 < nq) p2 <<= 1; S = 32 / p2; }
-        const int sl = lane % S;
-        for (int q0 = 0; q0 < nq; q0 += 32 / S) {
-            const int qi = q0 + lane / S;
-            const bool valid = qi < nq;
-            double qx = 0, qy = 0, qz = 0;
-            if (valid) {
-                qx = meanA[3 * (size_t)(qbase + qi)];
-                qy = meanA[3 * (size_t)(qbase + qi) + 1];
-                qz = meanA[3 * (size_t)(qbase + qi) + 2];
+    for (int64_t base = ((int64_t)blockIdx.x * 8 + w) * 32; base < n_rows; base += (int64_t)gridDim.x * 256) {
+        const int64_t r = base + lane;
+        bool valid = r < n_rows;
+        const int a = valid ? row_brick[r] : 0;
+        if (n_shards > 1 && (a % n_shards) != shard) valid = false;
+        if (!__any_sync(0xFFFFFFFFu, valid)) continue;
+        const float4 ql = valid ? locA[r] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float gm2[3] = {fmaxf(ql.x - slack, 0.f), fmaxf(ql.y - slack, 0.f), fmaxf(ql.z - slack, 0.f)};
+        float gp2[3] = {fmaxf(edge_f - ql.x - slack, 0.f), fmaxf(edge_f - ql.y - slack, 0.f), fmaxf(edge_f - ql.z - slack, 0.f)};
+        #pragma unroll
+        for (int d = 0; d < 3; ++d) { gm2[d] *= gm2[d]; gp2[d] *= gp2[d]; }
+        const unsigned present = valid ? (unsigned)abn[(size_t)a * 32 + 27].x : 0u;
+        __syncwarp();
+        S.ql[lane] = ql;
+        S.brick[lane] = a;
+        S.best[lane] = (unsigned long long)__double_as_longlong(1e300);
+        double best = 1e300;
+        #pragma unroll 1
+        for (int round = 0; round < 3; ++round) {
+            // the bricks of this round my query still needs
+            unsigned m = present & kRoundMask[round];
+            if (round > 0 && m) {
+                const float blf = best < 1e30 ? (float)best : 3.0e38f;
+                unsigned keep = 0;
+                for (unsigned mm = m; mm;) {
+                    const int nb = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    if (nn_gap2(nb, gm2, gp2) < blf) keep |= 1u << nb;
+                }
+                m = keep;
             }
-            // offset of the query inside its brick (x, y, z)
-            const double lx = qx - (g.mn[0] + (double)bx * edge), ly = qy - (g.mn[1] + (double)by * edge),
-                         lz = qz - (g.mn[2] + (double)bz * edge);
-            const float qlx = (float)lx, qly = (float)ly, qlz = (float)lz, edge_f = (float)edge;
-            // per-axis gaps to the neighbouring bricks in float32 (pruning bound only; made conservative by `slack`)
-            const float gm[3] = {fmaxf((float)(lx - slack), 0.f), fmaxf((float)(ly - slack), 0.f), fmaxf((float)(lz - slack), 0.f)};
-            const float gp[3] = {fmaxf((float)(edge - lx - slack), 0.f), fmaxf((float)(edge - ly - slack), 0.f),
-                                 fmaxf((float)(edge - lz - slack), 0.f)};
-            double best = 1e300;
-            #pragma unroll 1
-            for (int step = 0; step < 27; ++step) {
-                const int nb = c_nn_order[step];                                     // centre, faces, edges, corners
-                if (!((present >> nb) & 1u)) continue;                               // warp-uniform
-                const int2 rc = make_int2(__shfl_sync(0xFFFFFFFFu, mine.x, nb), __shfl_sync(0xFFFFFFFFu, mine.y, nb));
-                const int dz = nb / 9 - 1, dy = (nb / 3) % 3 - 1, dx = nb % 3 - 1;
-                const float gx = dx == 0 ? 0.f : (dx < 0 ? gm[0] : gp[0]), gy = dy == 0 ? 0.f : (dy < 0 ? gm[1] : gp[1]),
-                            gz = dz == 0 ? 0.f : (dz < 0 ? gm[2] : gp[2]);
-                const float lb2 = (gx * gx + gy * gy + gz * gz) * 0.999999f;       // never above the true bound
-                if (__all_sync(0xFFFFFFFFu, !valid || best <= (double)lb2)) continue;
-                // float32 screening in brick-local coordinates (|coordinate| < 3 brick edges, error ~2e-6 relative on
-                // d^2); every candidate that could beat the current best is re-evaluated in float64
-                const double* c = meanB + 3 * (size_t)rc.x;
-                const float4* cl = locB + (size_t)rc.x;
-                const float sx = qlx - (float)dx * edge_f, sy = qly - (float)dy * edge_f, sz = qlz - (float)dz * edge_f;
-                double bl = best;
-                float blf = (bl < 1e30) ? (float)bl * 1.00002f : 3.0e38f;
-                for (int i = sl; i < rc.y; i += S) {
-                    const float4 p = __ldg(cl + i);
-                    const float fx = sx - p.x, fy = sy - p.y, fz = sz - p.z;
-                    const float d2f = fx * fx + fy * fy + fz * fz;
-                    if (d2f <= blf) {
-                        double ex = qx - c[3 * i], ey = qy - c[3 * i + 1], ez = qz - c[3 * i + 2];
-                        bl = fmin(bl, ex * ex + ey * ey + ez * ez);
-                        blf = (float)bl * 1.00002f;
+            const int cnt = __popc(m);
+            int incl = cnt;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            if (total == 0) continue;
+            int off = incl - cnt;
+            while (m) {
+                const int nb = __ffs(m) - 1;
+                m &= m - 1;
+                S.list[off++] = (uint16_t)((lane << 5) | nb);
+            }
+            __syncwarp();
+            const int grp = lane >> 2, sub = lane & 3;
+            for (int k0 = 0; k0 < total; k0 += 8) {
+                const int k = k0 + grp;
+                const bool on = k < total;
+                double bl = 1e300, cur = 1e300;
+                int o = 0;
+                if (on) {
+                    const int e = S.list[k];
+                    o = e >> 5;
+                    const int nb = e & 31;
+                    cur = __longlong_as_double((long long)S.best[o]);
+                    bl = cur;
+                    const float4 q = S.ql[o];
+                    const int2 rc = abn[(size_t)S.brick[o] * 32 + nb];
+                    const int dz = nb / 9 - 1, dy = (nb / 3) % 3 - 1, dx = nb % 3 - 1;
+                    const float sx = q.x - (float)dx * edge_f, sy = q.y - (float)dy * edge_f, sz = q.z - (float)dz * edge_f;
+                    const double* qd = meanA + 3 * (base + o);
+                    const double* c = meanB + 3 * (size_t)rc.x;
+                    const float4* cl = locB + (size_t)rc.x;
+                    float blf = bl < 1e30 ? (float)bl * 1.00002f : 3.0e38f;
+                    for (int i = sub; i < rc.y; i += 4) {
+                        const float4 p = __ldg(cl + i);
+                        const float fx = sx - p.x, fy = sy - p.y, fz = sz - p.z;
+                        const float d2f = fx * fx + fy * fy + fz * fz;
+                        if (d2f <= blf) {                       // float32 error ~2e-6 relative: could win -> float64
+                            const double ex = qd[0] - c[3 * i], ey = qd[1] - c[3 * i + 1], ez = qd[2] - c[3 * i + 2];
+                            bl = fmin(bl, ex * ex + ey * ey + ez * ez);
+                            blf = (float)bl * 1.00002f;
+                        }
                     }
                 }
-                for (int d = 1; d < S; d <<= 1) bl = fmin(bl, __shfl_xor_sync(0xFFFFFFFFu, bl, d));
-                best = bl;
+                bl = fmin(bl, __shfl_xor_sync(0xFFFFFFFFu, bl, 1));
+                bl = fmin(bl, __shfl_xor_sync(0xFFFFFFFFu, bl, 2));
+                if (on && sub == 0 && bl < cur) atomicMin(&S.best[o], (unsigned long long)__double_as_longlong(bl));
             }
-            if (valid && sl == 0) {
-                int ring = 1;
-                if (best > edge * edge) ++fb;
-                while (best > (double)ring * edge * (double)ring * edge && ring < max_ring) {
-                    ++ring;
-                    for (int dz = -ring; dz <= ring; ++dz)
-                        for (int dy = -ring; dy <= ring; ++dy) {
-                            const bool shell = (abs(dz) == ring) || (abs(dy) == ring);
-                            for (int dx = -ring; dx <= ring; dx += (shell ? 1 : 2 * ring)) {
-                                int z = bz + dz, y = by + dy, x = bx + dx;
-                                if (z < 0 || y < 0 || x < 0 || z > 65535 || y > 65535 || x > 65535) continue;
-                                int id = hash_find(hB, pack_key(0u, (uint32_t)z, (uint32_t)y, (uint32_t)x));
-                                if (id < 0) continue;
-                                const int cb = B[id].base, cn = B[id].count;
-                                for (int i = 0; i < cn; ++i) {
-                                    double ex = qx - meanB[3 * (size_t)(cb + i)], ey = qy - meanB[3 * (size_t)(cb + i) + 1],
-                                           ez = qz - meanB[3 * (size_t)(cb + i) + 2];
-                                    best = fmin(best, ex * ex + ey * ey + ez * ez);
-                                }
+            __syncwarp();
+            best = __longlong_as_double((long long)S.best[lane]);
+        }
+        if (valid && best > edge * edge) {                                         // exact ring fallback (rare)
+            ++fb;
+            const double qx = meanA[3 * r], qy = meanA[3 * r + 1], qz = meanA[3 * r + 2];
+            const uint64_t key = A[a].key;
+            const int bz = (int)key_z(key), by = (int)key_y(key), bx = (int)key_x(key);
+            int ring = 1;
+            while (best > (double)ring * edge * (double)ring * edge && ring < max_ring) {
+                ++ring;
+                for (int dz = -ring; dz <= ring; ++dz)
+                    for (int dy = -ring; dy <= ring; ++dy) {
+                        const bool shell = (abs(dz) == ring) || (abs(dy) == ring);
+                        for (int dx = -ring; dx <= ring; dx += (shell ? 1 : 2 * ring)) {
+                            int z = bz + dz, y = by + dy, x = bx + dx;
+                            if (z < 0 || y < 0 || x < 0 || z > 65535 || y > 65535 || x > 65535) continue;
+                            int id = hash_find(hB, pack_key(0u, (uint32_t)z, (uint32_t)y, (uint32_t)x));
+                            if (id < 0) continue;
+                            const int cb = B[id].base, cn = B[id].count;
+                            for (int i = 0; i < cn; ++i) {
+                                double ex = qx - meanB[3 * (size_t)(cb + i)], ey = qy - meanB[3 * (size_t)(cb + i) + 1],
+                                       ez = qz - meanB[3 * (size_t)(cb + i) + 2];
+                                best = fmin(best, ex * ex + ey * ey + ez * ez);
                             }
                         }
-                }
-                local_sum += best;
+                    }
             }
         }
+        if (valid) local_sum += best;
     }
     #pragma unroll
     for (int d = 16; d > 0; d >>= 1) local_sum += __shfl_xor_sync(0xFFFFFFFFu, local_sum, d);
     fb = __reduce_add_sync(0xFFFFFFFFu, fb);
-    if (lane == 0) s_red[threadIdx.x >> 5] = local_sum;
+    if (lane == 0) s_red[w] = local_sum;
     if (lane == 0 && fb) atomicAdd(n_fallback, (unsigned long long)fb);
     __syncthreads();
     if (threadIdx.x == 0) {
         double t = 0.0;
-        for (int w = 0; w < kNNThreads / 32; ++w) t += s_red[w];
+        for (int i = 0; i < 8; ++i) t += s_red[i];
         atomicAdd(acc, t);
     }
 }
@@ -313,6 +363,8 @@ struct VoxelMeans {
     GridMap gm;
     DBuf<double> mean;         // [rows][3]
     DBuf<float4> loc;          // [rows] mean relative to its brick origin, float32
+    DBuf<int32_t> row_brick;   // [rows] brick of every voxel mean
+    DBuf<uint16_t> row_pos;
 };
 
 static void voxel_means(Ctx& cx, const float* d_P, int64_t n, const double mn[3], double voxel, VoxelMeans& vm) {
@@ -326,6 +378,9 @@ static void voxel_means(Ctx& cx, const float* d_P, int64_t n, const double mn[3]
     cnt.zero();
     k_voxel_accumulate<<<div_up(n, 256), 256, 0, st>>>(d_P, vm.gm.pt_row.p, n, vm.mean.p, cnt.p);
     k_voxel_mean<<<div_up(rows, 256), 256, 0, st>>>(vm.mean.p, cnt.p, rows);
+    vm.row_brick.alloc(rows, st);
+    vm.row_pos.alloc(rows, st);
+    brickmap_expand_rows(cx, vm.gm.map, vm.row_brick.p, vm.row_pos.p);
     vm.loc.alloc(rows, st);
     k_local_means<<<div_up((int64_t)vm.gm.map.n_bricks * 32, 256), 256, 0, st>>>(vm.gm.map.bricks.p, vm.gm.map.n_bricks, vm.mean.p,
                                                                                  vm.gm.g, vm.loc.p);
@@ -366,12 +421,14 @@ void chamfer_partial(Ctx& cx, const float* d_P, int64_t np, const float* d_Q, in
                                                                       B.gm.map.bricks.p, abn.p);
     k_cross_neighbours<<<div_up((int64_t)nB * 32, 256), 256, 0, st>>>(B.gm.map.bricks.p, nB, A.gm.map.view(),
                                                                       A.gm.map.bricks.p, ban.p);
-    int gA = std::max(1, std::min(div_up(div_up(nA, n_shards), kNNThreads / 32), kNumSMs * 8));
-    int gB = std::max(1, std::min(div_up(div_up(nB, n_shards), kNNThreads / 32), kNumSMs * 8));
-    k_nn_sqdist<<<gA, kNNThreads, 0, st>>>(A.gm.map.bricks.p, nA, A.mean.p, abn.p, B.gm.map.view(), B.gm.map.bricks.p,
-                                           B.mean.p, B.loc.p, A.gm.g, max_ring, shard, n_shards, acc.p, nfb.p);
-    k_nn_sqdist<<<gB, kNNThreads, 0, st>>>(B.gm.map.bricks.p, nB, B.mean.p, ban.p, A.gm.map.view(), A.gm.map.bricks.p,
-                                           A.mean.p, A.loc.p, A.gm.g, max_ring, shard, n_shards, acc.p + 1, nfb.p + 1);
+    const int64_t rA = A.gm.map.n_rows, rB = B.gm.map.n_rows;
+    int gA = (int)std::max<int64_t>(1, std::min<int64_t>(div_up(rA, 256), kNumSMs * 16));
+    int gB = (int)std::max<int64_t>(1, std::min<int64_t>(div_up(rB, 256), kNumSMs * 16));
+    k_nn_sqdist_pairs<<<gA, 256, 0, st>>>(A.gm.map.bricks.p, A.row_brick.p, rA, A.mean.p, A.loc.p, abn.p, B.gm.map.view(),
+                                        B.gm.map.bricks.p, B.mean.p, B.loc.p, A.gm.g, max_ring, shard, n_shards, acc.p, nfb.p);
+    k_nn_sqdist_pairs<<<gB, 256, 0, st>>>(B.gm.map.bricks.p, B.row_brick.p, rB, B.mean.p, B.loc.p, ban.p, A.gm.map.view(),
+                                        A.gm.map.bricks.p, A.mean.p, A.loc.p, A.gm.g, max_ring, shard, n_shards, acc.p + 1,
+                                        nfb.p + 1);
     cx.launches += 4;
     if (Trace::enabled()) {
         auto f = nfb.to_host();
