@@ -132,6 +132,44 @@ int  sqsm_radius_graph(sqsm_handle h, double r, int64_t* n_edges, int64_t* h_edg
 int  sqsm_radius_graph_points(sqsm_handle h, const float* h_points_xyz, int64_t m, double r,
                               int64_t* n_edges, int64_t* h_edges_ij, int64_t capacity);
 
+/* ---- cloud preparation in front of the path ---------------------
+ * Replaces entrypoints/smartqsm.py:882-913: bounding box -> global shift -> translate (:882-888),
+ * Open3D voxel_down_sample, float64 voxel means (:889), Open3D remove_statistical_outlier
+ * (:895-898), density-adaptation scale = voxel_down_size / mean nearest-neighbour distance
+ * (SciPy KDTree, :908-913).  Output order: 8^3-voxel bricks by (z, y, x) brick index, then z, y, x
+ * inside the brick (Open3D's unordered_map order is not reproducible).  filter ==
+ * "radius_outlier_removal" (:899-902) is not provided (no shipped config uses it). */
+typedef struct SqsmPrepConfig {
+    double  voxel_down_size;      /* configs/*.yaml: voxel_down_size (0.01) */
+    double  std_ratio;            /* kwargs_for_filter.std_ratio (4.0) */
+    int32_t filter;               /* 0 = none, 1 = statistical_outlier_removal */
+    int32_t nb_neighbors;         /* kwargs_for_filter.nb_neighbors (10); 1..32 */
+    int32_t density_adaptation;   /* using_density_adaptation_in_skeletonization */
+    int32_t keep_debug;           /* keep the intermediate arrays for sqsm_debug_prepared */
+    int32_t reserved[4];
+} SqsmPrepConfig;
+
+typedef struct SqsmPrepStats {
+    int64_t n_in, n_voxel, n_kept, gpu_launches;
+    double  global_shift[3];      /* smartqsm.py:883-887 */
+    double  scale;                /* 1.0 without density adaptation */
+    double  mean_nn;              /* mean distance to the nearest other point of the kept cloud */
+    double  cloud_mean, std_dev, threshold;   /* statistics of remove_statistical_outlier */
+    float   ms_total, ms_downsample, ms_filter, ms_scale;
+} SqsmPrepStats;
+
+/* Runs the whole preparation on host float64 N x 3 points; the prepared cloud stays on the device. */
+int  sqsm_prepare_cloud_f64(sqsm_handle h, const double* h_points_xyz, int64_t n,
+                            const SqsmPrepConfig* cfg, SqsmPrepStats* stats);
+int  sqsm_prepared_size(sqsm_handle h, int64_t* n_kept, int64_t* n_voxel);
+/* The cloud the reference holds in `points` after :904 (shifted, down-sampled, filtered; NOT scaled). */
+int  sqsm_get_prepared(sqsm_handle h, double* h_points_xyz);
+/* CoreAlgorithmBase.input(points = prepared * scale) without the host round trip (:922 + epoch-1 cast). */
+int  sqsm_set_points_prepared(sqsm_handle h);
+/* keep_debug only: voxel means float64[n_voxel,3], avg k-NN distance float64[n_voxel], keep uint8[n_voxel]
+ * (the last two only with filter == 1); any pointer may be NULL. */
+int  sqsm_debug_prepared(sqsm_handle h, double* h_voxel_means, double* h_avg_distance, uint8_t* h_keep);
+
 /* ---- parity / inspection hooks (integer outputs of the LAST sqsm_contract_step) --------
  * Rows are reported in CANONICAL order: by cube sample, then ascending
  * winning point index.  Enable capture before the step; it keeps the per-level tables. */

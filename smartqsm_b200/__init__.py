@@ -2,7 +2,8 @@
 
 Only the pieces that path needs live here: ``csrc/`` (CUDA kernels + the C ABI of
 ``libsqsm_b200.so``), ``_lib`` (ctypes binding), ``core_algorithms`` (mirror of the reference's
-plug-in interface), ``sharding`` (tree-sharded multi-GPU driver) and ``synthetic`` (seeded inputs).
+plug-in interface), ``preprocess`` (the cloud preparation in front of the path), ``sharding``
+(tree-sharded multi-GPU driver) and ``synthetic`` (seeded inputs).
 There is no CPU fallback: creating an engine without the built library or without an sm_100 GPU
 raises.
 """
@@ -13,6 +14,9 @@ def __getattr__(name):
     if name in ("SpconvBasedContraction", "CoreAlgorithmBase", "registry", "register_into", "load_checkpoint"):
         from . import core_algorithms
         return getattr(core_algorithms, name)
+    if name in ("prepare_cloud", "PreparedCloud"):
+        from . import preprocess
+        return getattr(preprocess, name)
     if name == "Engine":
         from ._lib import Engine
         return Engine

@@ -40,6 +40,27 @@ class SqsmIterStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class SqsmPrepConfig(C.Structure):
+    _fields_ = [
+        ("voxel_down_size", C.c_double), ("std_ratio", C.c_double), ("filter", C.c_int32), ("nb_neighbors", C.c_int32),
+        ("density_adaptation", C.c_int32), ("keep_debug", C.c_int32), ("reserved", C.c_int32 * 4),
+    ]
+
+
+class SqsmPrepStats(C.Structure):
+    _fields_ = [
+        ("n_in", C.c_int64), ("n_voxel", C.c_int64), ("n_kept", C.c_int64), ("gpu_launches", C.c_int64),
+        ("global_shift", C.c_double * 3), ("scale", C.c_double), ("mean_nn", C.c_double),
+        ("cloud_mean", C.c_double), ("std_dev", C.c_double), ("threshold", C.c_double),
+        ("ms_total", C.c_float), ("ms_downsample", C.c_float), ("ms_filter", C.c_float), ("ms_scale", C.c_float),
+    ]
+
+    def as_dict(self) -> dict:
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["global_shift"] = np.array(list(self.global_shift), dtype=np.float64)
+        return d
+
+
 EXPORTS = [
     "sqsm_create", "sqsm_destroy", "sqsm_last_error", "sqsm_abi_version", "sqsm_set_weight",
     "sqsm_finalize_weights", "sqsm_set_points_f64", "sqsm_set_points_dev_f32", "sqsm_set_state_f32", "sqsm_contract_step",
@@ -49,6 +70,7 @@ EXPORTS = [
     "sqsm_debug_batch_shapes", "sqsm_debug_level_tables", "sqsm_debug_canon_to_internal",
     "sqsm_debug_predictions", "sqsm_debug_features", "sqsm_profile_reset", "sqsm_profile_get",
     "sqsm_profile_enable", "sqsm_profile_families", "sqsm_timer_start", "sqsm_timer_stop", "sqsm_launch_count",
+    "sqsm_prepare_cloud_f64", "sqsm_prepared_size", "sqsm_get_prepared", "sqsm_set_points_prepared", "sqsm_debug_prepared",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -102,6 +124,11 @@ def load_library() -> C.CDLL:
         "sqsm_timer_stop": ([vp, P(f64)], C.c_int),
         "sqsm_launch_count": ([vp, P(i64)], C.c_int),
         "sqsm_profile_enable": ([vp, i32], C.c_int),
+        "sqsm_prepare_cloud_f64": ([vp, vp, i64, P(SqsmPrepConfig), P(SqsmPrepStats)], C.c_int),
+        "sqsm_prepared_size": ([vp, P(i64), P(i64)], C.c_int),
+        "sqsm_get_prepared": ([vp, vp], C.c_int),
+        "sqsm_set_points_prepared": ([vp], C.c_int),
+        "sqsm_debug_prepared": ([vp, vp, vp, vp], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, name)
@@ -168,6 +195,37 @@ class Engine:
 
     def set_points_device_f32(self, dev_ptr: int, n: int) -> None:
         self._check(self._lib.sqsm_set_points_dev_f32(self._h, C.c_void_p(dev_ptr), n), "set_points_dev")
+
+    # ---- cloud preparation (row f2)
+    def prepare_cloud(self, points: np.ndarray, *, voxel_down_size: float = 0.01, filter: int = 1, nb_neighbors: int = 10,
+                      std_ratio: float = 4.0, density_adaptation: bool = True, keep_debug: bool = False) -> dict:
+        a = np.ascontiguousarray(points, dtype=np.float64)
+        assert a.ndim == 2 and a.shape[1] == 3
+        cfg = SqsmPrepConfig(voxel_down_size=voxel_down_size, std_ratio=std_ratio, filter=int(filter),
+                             nb_neighbors=int(nb_neighbors), density_adaptation=int(density_adaptation),
+                             keep_debug=int(keep_debug))
+        st = SqsmPrepStats()
+        self._check(self._lib.sqsm_prepare_cloud_f64(self._h, _ptr(a), a.shape[0], C.byref(cfg), C.byref(st)), "prepare_cloud")
+        return st.as_dict()
+
+    def prepared_points(self) -> np.ndarray:
+        n = C.c_int64()
+        self._check(self._lib.sqsm_prepared_size(self._h, C.byref(n), None), "prepared_size")
+        out = np.empty((n.value, 3), dtype=np.float64)
+        self._check(self._lib.sqsm_get_prepared(self._h, _ptr(out)), "get_prepared")
+        return out
+
+    def set_points_prepared(self) -> None:
+        self._check(self._lib.sqsm_set_points_prepared(self._h), "set_points_prepared")
+
+    def debug_prepared(self, with_filter: bool = True):
+        n, nv = C.c_int64(), C.c_int64()
+        self._check(self._lib.sqsm_prepared_size(self._h, C.byref(n), C.byref(nv)), "prepared_size")
+        vox = np.empty((nv.value, 3), dtype=np.float64)
+        avg = np.empty(nv.value, dtype=np.float64) if with_filter else None
+        keep = np.empty(nv.value, dtype=np.uint8) if with_filter else None
+        self._check(self._lib.sqsm_debug_prepared(self._h, _ptr(vox), _ptr(avg), _ptr(keep)), "debug_prepared")
+        return vox, avg, keep
 
     def set_state(self, points_f32: np.ndarray, disp_f32: np.ndarray) -> None:
         p = np.ascontiguousarray(points_f32, dtype=np.float32)

@@ -114,6 +114,7 @@ class SpconvBasedContraction(CoreAlgorithmBase):
         self._early_stopped = False
         self._points: Optional[np.ndarray] = None
         self._loaded = False
+        self._prepared = False
         self._host: Optional[Tuple[np.ndarray, np.ndarray]] = None
         self.history: List[dict] = []
 
@@ -121,16 +122,40 @@ class SpconvBasedContraction(CoreAlgorithmBase):
         super().input(**kwargs)
         if "points" in kwargs:
             self._loaded = False
+            self._prepared = False
             self._epoch = 0
             self._host = None
             self.history = []
 
+    def prepare_input(self, raw_points: np.ndarray, *, voxel_down_size: float = 0.01, filter: Optional[str] = None,
+                      kwargs_for_filter: Optional[Dict[str, Any]] = None,
+                      using_density_adaptation_in_skeletonization: bool = False):
+        """``entrypoints/smartqsm.py:882-922`` on this algorithm's engine: shift, voxel
+        down-sampling, outlier filter, density scale, then ``input(points = prepared * scale)`` without the host
+        round trip.  Returns the :class:`~smartqsm_b200.preprocess.PreparedCloud` (``points``, ``global_shift``,
+        ``scale``) the entry point needs afterwards (``skeletal_points / scale``, ``:940-941``)."""
+        from .preprocess import prepare_cloud
+        prepared = prepare_cloud(raw_points, voxel_down_size=voxel_down_size, filter=filter,
+                                 kwargs_for_filter=kwargs_for_filter,
+                                 using_density_adaptation_in_skeletonization=using_density_adaptation_in_skeletonization,
+                                 engine=self._engine)
+        self._points = None
+        self._loaded = False
+        self._prepared = True
+        self._epoch = 0
+        self._host = None
+        self.history = []
+        return prepared
+
     def _contract(self):
         self._epoch += 1
         if not self._loaded:                       # epoch 1: float64 -> float32 copy, zero displacements (:81-83)
-            if self._points is None:
+            if self._prepared:
+                self._engine.set_points_prepared()
+            elif self._points is None:
                 raise RuntimeError("input(points=...) was not called")
-            self._engine.set_points(self._points)
+            else:
+                self._engine.set_points(self._points)
             self._loaded = True
         st = self._engine.contract_step()
         self.history.append(st)

@@ -49,6 +49,7 @@ struct sqsm_engine {
     double edges_r = -1.0;
     int64_t max_entries_per_pass = 48ll << 20;
     size_t pool_reserved = 0;
+    PrepState prep;
 };
 
 static std::string g_create_error;
@@ -199,6 +200,70 @@ extern "C" int sqsm_set_points_dev_f32(sqsm_handle h, const float* d_xyz, int64_
     reset_state(h);
     SQSM_CUDA(cudaStreamSynchronize(st));
     reserve_pool(h, n);
+    SQSM_API_END(h)
+}
+
+// ---- cloud preparation (row f2)
+extern "C" int sqsm_prepare_cloud_f64(sqsm_handle h, const double* xyz, int64_t n, const SqsmPrepConfig* cfg, SqsmPrepStats* stats) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(cfg != nullptr, "null SqsmPrepConfig");
+    h->prep.valid = false;
+    SqsmPrepStats st_local;
+    prepare_cloud(h->cx, xyz, n, *cfg, h->prep, st_local);
+    if (stats) *stats = st_local;
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_prepared_size(sqsm_handle h, int64_t* n_kept, int64_t* n_voxel) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(h->prep.valid, "no prepared cloud: call sqsm_prepare_cloud_f64 first");
+    if (n_kept) *n_kept = h->prep.n_kept;
+    if (n_voxel) *n_voxel = h->prep.n_voxel;
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_get_prepared(sqsm_handle h, double* xyz) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(h->prep.valid && xyz, "no prepared cloud / null output");
+    SQSM_CUDA(cudaMemcpyAsync(xyz, h->prep.pts.p, sizeof(double) * h->prep.n_kept * 3, cudaMemcpyDeviceToHost, h->cx.st));
+    SQSM_CUDA(cudaStreamSynchronize(h->cx.st));
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_set_points_prepared(sqsm_handle h) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(h->prep.valid, "no prepared cloud: call sqsm_prepare_cloud_f64 first");
+    cudaStream_t st = h->cx.st;
+    const int64_t n = h->prep.n_kept;
+    h->P.alloc(n * 3, st);
+    h->D.alloc(n * 3, st);
+    h->D.zero();
+    prepared_to_f32(h->cx, h->prep, h->P.p);
+    h->n = n;
+    reset_state(h);
+    SQSM_CUDA(cudaStreamSynchronize(st));
+    reserve_pool(h, n);
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_debug_prepared(sqsm_handle h, double* vox, double* avg, uint8_t* keep) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(h->prep.valid, "no prepared cloud");
+    cudaStream_t st = h->cx.st;
+    const int64_t nv = h->prep.n_voxel;
+    if (vox) {
+        SQSM_CHECK(h->prep.vox.n == nv * 3, "voxel means were not kept (keep_debug = 0)");
+        SQSM_CUDA(cudaMemcpyAsync(vox, h->prep.vox.p, sizeof(double) * nv * 3, cudaMemcpyDeviceToHost, st));
+    }
+    if (avg) {
+        SQSM_CHECK(h->prep.avg.n == nv, "avg distances were not kept (keep_debug = 0 or filter = 0)");
+        SQSM_CUDA(cudaMemcpyAsync(avg, h->prep.avg.p, sizeof(double) * nv, cudaMemcpyDeviceToHost, st));
+    }
+    if (keep) {
+        SQSM_CHECK(h->prep.keep.n == nv, "keep flags were not kept (keep_debug = 0 or filter = 0)");
+        SQSM_CUDA(cudaMemcpyAsync(keep, h->prep.keep.p, nv, cudaMemcpyDeviceToHost, st));
+    }
+    SQSM_CUDA(cudaStreamSynchronize(st));
     SQSM_API_END(h)
 }
 

@@ -123,4 +123,16 @@ struct SkeletalResult {
 void skeletal_sample(Ctx& cx, const float* d_P, const float* d_D, int64_t n, double voxel, SkeletalResult& out);
 void radius_graph(Ctx& cx, const float* d_pts, int64_t m, double r, DBuf<int64_t>& edges, int64_t* n_edges);
 
+// preprocess.cu (row f2: entrypoints/smartqsm.py:882-913)
+struct PrepState {
+    DBuf<double> pts;                   // [n_kept][3] shifted, down-sampled, filtered (not scaled)
+    DBuf<double> vox, avg;              // keep_debug: voxel means [n_voxel][3], avg k-NN distance [n_voxel]
+    DBuf<uint8_t> keep;                 // keep_debug: filter decision per voxel mean
+    int64_t n_kept = 0, n_voxel = 0;
+    double scale = 1.0;
+    bool valid = false;
+};
+void prepare_cloud(Ctx& cx, const double* h_xyz, int64_t n, const SqsmPrepConfig& cfg, PrepState& ps, SqsmPrepStats& out);
+void prepared_to_f32(Ctx& cx, const PrepState& ps, float* d_out);
+
 }  // namespace sqsm

@@ -86,3 +86,18 @@ def rel_err(a: np.ndarray, b: np.ndarray) -> float:
     if a.size == 0:
         return 0.0
     return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64))) / max(float(np.max(np.abs(b))), 1e-30))
+
+
+def make_raw_scan(n_surface: int, seed: int, leaf_on: bool = False, outliers: int = 200) -> np.ndarray:
+    """A raw scan as the entry point would read it from disk (input of ``smartqsm.py:882``): several noisy
+    returns per surface point, a sprinkle of far outliers, projected (UTM-like) coordinates, shuffled."""
+    from smartqsm_b200.synthetic import make_tree
+    pts = make_tree(n_surface, seed, leaf_on)
+    rng = np.random.default_rng(seed)
+    extra = pts[rng.integers(0, len(pts), len(pts) // 2)]
+    lo, hi = pts.min(axis=0), pts.max(axis=0)
+    raw = np.concatenate([pts + rng.normal(0, 0.002, pts.shape), extra + rng.normal(0, 0.003, extra.shape),
+                          rng.uniform(lo - 1.0, hi + 1.0, (outliers, 3))])
+    raw += np.array([351234.5, 5412345.25, 102.75])
+    rng.shuffle(raw)
+    return np.ascontiguousarray(raw)
