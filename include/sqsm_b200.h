@@ -151,6 +151,7 @@ typedef struct SqsmPrepConfig {
 
 typedef struct SqsmPrepStats {
     int64_t n_in, n_voxel, n_kept, gpu_launches;
+    int64_t n_far_filter, n_far_scale;   /* queries that needed the far (ring) search in each k-NN pass */
     double  global_shift[3];      /* smartqsm.py:883-887 */
     double  scale;                /* 1.0 without density adaptation */
     double  mean_nn;              /* mean distance to the nearest other point of the kept cloud */

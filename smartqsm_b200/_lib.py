@@ -50,7 +50,7 @@ class SqsmPrepConfig(C.Structure):
 class SqsmPrepStats(C.Structure):
     _fields_ = [
         ("n_in", C.c_int64), ("n_voxel", C.c_int64), ("n_kept", C.c_int64), ("gpu_launches", C.c_int64),
-        ("global_shift", C.c_double * 3), ("scale", C.c_double), ("mean_nn", C.c_double),
+        ("n_far_filter", C.c_int64), ("n_far_scale", C.c_int64), ("global_shift", C.c_double * 3), ("scale", C.c_double), ("mean_nn", C.c_double),
         ("cloud_mean", C.c_double), ("std_dev", C.c_double), ("threshold", C.c_double),
         ("ms_total", C.c_float), ("ms_downsample", C.c_float), ("ms_filter", C.c_float), ("ms_scale", C.c_float),
     ]

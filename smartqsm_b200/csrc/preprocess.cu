@@ -14,6 +14,7 @@
 // key (z, y, x), then z, y, x inside the brick); Open3D's own order is that of a std::unordered_map and not reproducible.
 #include "engine.h"
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace sqsm {
@@ -148,13 +149,14 @@ struct KnnBest {
 
 // Exact k nearest neighbours (the query itself included, like a KD-tree query at a cloud point) over the voxel means.
 // Thread per query; bricks nearest first with a float64 lower bound against the current k-th distance; after the 27
-// bricks everything else is at least one brick edge away, so rings of bricks are added while the k-th distance exceeds
-// the ring bound.  mode 0: mean of the k distances (Open3D avg_distances); mode 1: distance to the nearest OTHER point.
+// bricks everything else is at least one brick edge away; a query whose k-th distance exceeds that bound (isolated
+// points - the very outliers the filter is after) is handed to k_knn_far.  mode 0: mean of the k distances (Open3D avg_distances); mode 1: distance to the nearest OTHER point.
 // `alive` (optional) restricts both queries and candidates to a subset of the rows.
 __global__ void __launch_bounds__(128) k_knn(const Brick* __restrict__ bricks, const int32_t* __restrict__ bnbr, BrickHash h,
                                              const int32_t* __restrict__ row_brick, const double* __restrict__ V,
                                              const uint8_t* __restrict__ alive, int64_t rows, int k,
-                                             const __grid_constant__ PrepGrid g, int max_ring, int mode, double* __restrict__ out) {
+                                             const __grid_constant__ PrepGrid g, int mode, double* __restrict__ out,
+                                             int32_t* __restrict__ far_list, int32_t* __restrict__ n_far) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     if (alive && !alive[r]) { out[r] = -1.0; return; }
@@ -188,20 +190,10 @@ __global__ void __launch_bounds__(128) k_knn(const Brick* __restrict__ bricks, c
         if ((gx * gx + gy * gy + gz * gz) * (1.0 - 1e-12) >= best.worst()) continue;
         scan(bricks[id].base, bricks[id].count);
     }
-    int ring = 1;
     const double near_edge = edge * (1.0 - 1e-9);
-    while (best.worst() > (double)ring * near_edge * (double)ring * near_edge && ring < max_ring) {
-        ++ring;
-        for (int dz = -ring; dz <= ring; ++dz)
-            for (int dy = -ring; dy <= ring; ++dy) {
-                const bool shell = (abs(dz) == ring) || (abs(dy) == ring);
-                for (int dx = -ring; dx <= ring; dx += (shell ? 1 : 2 * ring)) {
-                    const int z = bz + dz, y = by + dy, x = bx + dx;
-                    if (z < 0 || y < 0 || x < 0 || z > 65535 || y > 65535 || x > 65535) continue;
-                    const int id = hash_find(h, pack_key(0u, (uint32_t)z, (uint32_t)y, (uint32_t)x));
-                    if (id >= 0) scan(bricks[id].base, bricks[id].count);
-                }
-            }
+    if (best.worst() > near_edge * near_edge) {           // not settled inside the 27 bricks: a warp finishes it (k_knn_far)
+        far_list[atomicAdd(n_far, 1)] = (int32_t)r;
+        return;
     }
     if (mode == 0) {
         double s = 0.0;
@@ -209,6 +201,115 @@ __global__ void __launch_bounds__(128) k_knn(const Brick* __restrict__ bricks, c
         out[r] = __ddiv_rn(s, (double)k);
     } else {
         out[r] = sqrt(best.d[1]);
+    }
+}
+
+// Deferred queries, one warp each: rings of bricks (hash probes) are scanned by the 32 lanes together until the k-th
+// distance is below the ring bound.  Every lane keeps its own sorted list; the warp-wide k smallest are read off by k
+// rounds of "minimum of the list heads", which also yields them in ascending order for the final sum.
+__device__ __forceinline__ double warp_min_f64(double v) {
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = fmin(v, __shfl_xor_sync(0xFFFFFFFFu, v, d));
+    return v;
+}
+struct BrickBitmap { const uint32_t* bits; int nx, ny, nz, wx; };      // occupancy of the brick lattice, x-major bit rows
+
+__global__ void __launch_bounds__(256) k_brick_bitmap(const Brick* __restrict__ bricks, int n_bricks, int ny, int wx,
+                                                      uint32_t* __restrict__ bits) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_bricks) return;
+    const uint64_t key = bricks[b].key;
+    const size_t w = ((size_t)key_z(key) * ny + key_y(key)) * wx + (key_x(key) >> 5);
+    atomicOr(&bits[w], 1u << (key_x(key) & 31));
+}
+
+__global__ void __launch_bounds__(128) k_knn_far(const Brick* __restrict__ bricks, BrickHash h, const int32_t* __restrict__ row_brick,
+                                                 const double* __restrict__ V, const uint8_t* __restrict__ alive, int k,
+                                                 const __grid_constant__ PrepGrid g, const __grid_constant__ BrickBitmap bm,
+                                                 int max_ring, int mode, const int32_t* __restrict__ far_list,
+                                                 const int32_t* __restrict__ n_far, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int n = *n_far;
+    const double edge = 8.0 * g.voxel, near_edge = edge * (1.0 - 1e-9);
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += (gridDim.x * blockDim.x) >> 5) {
+        const int64_t r = far_list[w];
+        const double qx = V[3 * r], qy = V[3 * r + 1], qz = V[3 * r + 2];
+        const uint64_t key = bricks[row_brick[r]].key;
+        const int bz = (int)key_z(key), by = (int)key_y(key), bx = (int)key_x(key);
+        KnnBest best;
+        best.init(k);
+        double bound = 1e300;                               // warp-wide k-th distance after the previous ring
+        auto scan_brick = [&](int z, int y, int x) {
+            const int id = hash_find(h, pack_key(0u, (uint32_t)z, (uint32_t)y, (uint32_t)x));
+            if (id < 0) return;
+            const int cb = bricks[id].base, cn = bricks[id].count;
+            for (int i = 0; i < cn; ++i) {
+                const size_t c = (size_t)(cb + i);
+                if (alive && !alive[c]) continue;
+                const double ex = qx - V[3 * c], ey = qy - V[3 * c + 1], ez = qz - V[3 * c + 2];
+                const double d2 = ex * ex + ey * ey + ez * ez;
+                if (d2 <= bound) best.push(d2);
+            }
+        };
+        for (int ring = 0; ring <= max_ring; ++ring) {
+            const int side = 2 * ring + 1;
+            for (int t = lane; t < side * side; t += 32) {
+                const int dz = t / side - ring, dy = t % side - ring;
+                const int z = bz + dz, y = by + dy;
+                if (z < 0 || y < 0 || z > 65535 || y > 65535) continue;
+                const bool shell = (abs(dz) == ring) || (abs(dy) == ring);
+                if (bm.bits != nullptr) {
+                    if (z >= bm.nz || y >= bm.ny) continue;
+                    const uint32_t* rowbits = bm.bits + ((size_t)z * bm.ny + y) * bm.wx;
+                    const int x0 = max(bx - ring, 0), x1 = min(bx + ring, bm.nx - 1);
+                    if (shell) {                                            // whole x row of the shell, 32 bricks per load
+                        for (int wd = x0 >> 5; wd <= (x1 >> 5); ++wd) {
+                            uint32_t m = rowbits[wd];
+                            const int lo = wd * 32;
+                            if (x0 > lo) m &= ~0u << (x0 - lo);
+                            if (x1 < lo + 31) m &= ~0u >> (lo + 31 - x1);
+                            while (m) {
+                                const int x = lo + __ffs(m) - 1;
+                                m &= m - 1;
+                                scan_brick(z, y, x);
+                            }
+                        }
+                    } else {                                                // only the two end caps
+                        if (bx - ring >= 0 && ((rowbits[(bx - ring) >> 5] >> ((bx - ring) & 31)) & 1u)) scan_brick(z, y, bx - ring);
+                        if (bx + ring < bm.nx && ((rowbits[(bx + ring) >> 5] >> ((bx + ring) & 31)) & 1u)) scan_brick(z, y, bx + ring);
+                    }
+                } else {
+                    for (int dx = -ring; dx <= ring; dx += (shell || ring == 0 ? 1 : 2 * ring)) {
+                        const int x = bx + dx;
+                        if (x < 0 || x > 65535) continue;
+                        scan_brick(z, y, x);
+                    }
+                }
+            }
+            // warp-wide k-th smallest
+            int pos = 0;
+            double kth = 1e300;
+            for (int j = 0; j < k; ++j) {
+                const double head = pos < k ? best.d[pos] : 1e300;
+                kth = warp_min_f64(head);
+                const unsigned who = __ballot_sync(0xFFFFFFFFu, head == kth);
+                if (lane == __ffs(who) - 1) ++pos;
+            }
+            bound = kth;
+            if (ring >= 1 && kth <= (double)ring * near_edge * (double)ring * near_edge) break;
+        }
+        // ascending read-out
+        int pos = 0;
+        double sum = 0.0, second = 0.0;
+        for (int j = 0; j < k; ++j) {
+            const double head = pos < k ? best.d[pos] : 1e300;
+            const double m = warp_min_f64(head);
+            const unsigned who = __ballot_sync(0xFFFFFFFFu, head == m);
+            if (lane == __ffs(who) - 1) ++pos;
+            sum = __dadd_rn(sum, sqrt(m));
+            if (j == 1) second = sqrt(m);
+        }
+        if (lane == 0) out[r] = mode == 0 ? __ddiv_rn(sum, (double)k) : second;
     }
 }
 
@@ -261,6 +362,19 @@ __global__ void __launch_bounds__(256) k_compact(const double* __restrict__ V, c
     out[3 * o] = V[3 * i];
     out[3 * o + 1] = V[3 * i + 1];
     out[3 * o + 2] = V[3 * i + 2];
+}
+
+void run_knn(Ctx& cx, const BrickMap& map, const BrickBitmap& bm, const int32_t* row_brick, const double* V, const uint8_t* alive,
+             int64_t rows, int k, const PrepGrid& g, int max_ring, int mode, double* out, int64_t* n_far_out) {
+    cudaStream_t st = cx.st;
+    DBuf<int32_t> far_list(rows, st), n_far(1, st);
+    n_far.zero();
+    k_knn<<<div_up(rows, 128), 128, 0, st>>>(map.bricks.p, map.bnbr.p, map.view(), row_brick, V, alive, rows, k, g, mode, out,
+                                              far_list.p, n_far.p);
+    k_knn_far<<<kNumSMs * 4, 128, 0, st>>>(map.bricks.p, map.view(), row_brick, V, alive, k, g, bm, max_ring, mode, far_list.p, n_far.p,
+                                            out);
+    cx.launches += 2;
+    if (n_far_out) *n_far_out = n_far.to_host()[0];
 }
 
 int bits_for(int64_t n) {
@@ -350,6 +464,8 @@ void prepare_cloud(Ctx& cx, const double* h_xyz, int64_t n, const SqsmPrepConfig
     // ---- search structure shared by the two neighbour queries
     const bool need_nn = cfg.filter == 1 || cfg.density_adaptation;
     DBuf<int32_t> row_brick;
+    DBuf<uint32_t> bitmap;
+    BrickBitmap bm{nullptr, 0, 0, 0, 0};
     int max_ring = 2;
     if (need_nn) {
         brickmap_build_neighbours(cx, map);
@@ -359,6 +475,20 @@ void prepare_cloud(Ctx& cx, const double* h_xyz, int64_t n, const SqsmPrepConfig
         double ext = 0;
         for (int a = 0; a < 3; ++a) ext = std::max(ext, mx[a] - mn[a]);
         max_ring = (int)std::ceil(ext / (8.0 * cfg.voxel_down_size)) + 2;
+        // brick occupancy bitmap for the far search (skipped when the lattice would need more than 256 MB)
+        const double edge = 8.0 * cfg.voxel_down_size;
+        int nb[3];
+        for (int a = 0; a < 3; ++a) nb[a] = (int)std::min(65536.0, std::floor((mx[a] - mn[a] + cfg.voxel_down_size) / edge) + 2.0);
+        const int wx = (nb[0] + 31) / 32;
+        const int64_t words = (int64_t)nb[2] * nb[1] * wx;
+        const char* no_bm = getenv("SQSM_PREP_NO_BITMAP");                 // test hook: force the hash-probe ring search
+        if (words <= (64ll << 20) && !(no_bm && no_bm[0] == '1')) {
+            bitmap.alloc(words, st);
+            bitmap.zero();
+            k_brick_bitmap<<<div_up(map.n_bricks, 256), 256, 0, st>>>(map.bricks.p, map.n_bricks, nb[1], wx, bitmap.p);
+            cx.launches++;
+            bm = BrickBitmap{bitmap.p, nb[0], nb[1], nb[2], wx};
+        }
     }
 
     // ---- remove_statistical_outlier (:895-898)
@@ -369,9 +499,7 @@ void prepare_cloud(Ctx& cx, const double* h_xyz, int64_t n, const SqsmPrepConfig
     if (cfg.filter == 1) {
         const int k = (int)std::min<int64_t>(cfg.nb_neighbors, rows);
         ps.avg.alloc(rows, st);
-        k_knn<<<div_up(rows, 128), 128, 0, st>>>(map.bricks.p, map.bnbr.p, map.view(), row_brick.p, V.p, nullptr, rows, k, g, max_ring,
-                                                  0, ps.avg.p);
-        cx.launches++;
+        run_knn(cx, map, bm, row_brick.p, V.p, nullptr, rows, k, g, max_ring, 0, ps.avg.p, &out.n_far_filter);
         const double cloud_mean = fixed_sum(cx, ps.avg.p, nullptr, rows, 0, 0.0) / (double)rows;
         const double sq = fixed_sum(cx, ps.avg.p, nullptr, rows, 1, cloud_mean);
         const double sd = rows > 1 ? std::sqrt(sq / (double)(rows - 1)) : 0.0;
@@ -404,9 +532,7 @@ void prepare_cloud(Ctx& cx, const double* h_xyz, int64_t n, const SqsmPrepConfig
     if (cfg.density_adaptation) {
         SQSM_CHECK(n_kept >= 2, "density adaptation needs at least two points");
         DBuf<double> nn(rows, st);
-        k_knn<<<div_up(rows, 128), 128, 0, st>>>(map.bricks.p, map.bnbr.p, map.view(), row_brick.p, V.p, cfg.filter == 1 ? keep.p : nullptr,
-                                                  rows, 2, g, max_ring, 1, nn.p);
-        cx.launches++;
+        run_knn(cx, map, bm, row_brick.p, V.p, cfg.filter == 1 ? keep.p : nullptr, rows, 2, g, max_ring, 1, nn.p, &out.n_far_scale);
         const double mean_nn = fixed_sum(cx, nn.p, nullptr, rows, 0, 0.0) / (double)n_kept;     // dropped rows hold -1, distances are > 0
         out.mean_nn = mean_nn;
         scale = cfg.voxel_down_size / mean_nn;

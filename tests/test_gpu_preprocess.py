@@ -42,6 +42,7 @@ def _check(engine, raw, **cfg):
 def test_prepare_cloud_matches_oracle(engine):
     st, ref = _check(engine, make_raw_scan(60000, 7))
     assert st["n_kept"] < st["n_voxel"], "the far outliers must be filtered"
+    assert st["n_far_filter"] > 0, "the sprinkled outliers must exercise the far search"
     assert st["gpu_launches"] > 0
 
 
@@ -62,6 +63,12 @@ def test_isolated_points_use_the_ring_search(engine):
     b = rng.normal(0, 0.02, (300, 3)) + [3.0, 0.5, 1.0]
     lone = np.array([[1.5, 0.2, 0.4], [0.7, -0.9, 2.0], [2.2, 1.4, 0.1]])
     _check(engine, np.concatenate([a, b, lone]), nb_neighbors=10, std_ratio=4.0)
+
+
+def test_far_search_without_the_occupancy_bitmap(engine, monkeypatch):
+    monkeypatch.setenv("SQSM_PREP_NO_BITMAP", "1")          # lattices too large for the bitmap probe the hash instead
+    st, _ = _check(engine, make_raw_scan(20000, 10))
+    assert st["n_far_filter"] > 0
 
 
 def test_hand_over_to_contraction_is_the_scaled_float32_cloud(engine):
