@@ -58,6 +58,9 @@ __global__ void k_make_idx(int* idx, int64_t n_chunks, int K, int64_t n_rows, in
         row = tile * 128 + r + delta;
         if (row < 0 || row >= n_rows) row = -1;
         if (pattern == 2 && (h & 1)) row = -1;
+        // pattern 3/4: absent rows (half / 62 %) are redirected to a pool of 4096 in-bounds "zero rows" spread over the table
+        if (pattern == 3 && (h & 1)) row = (int64_t)(((h >> 8) & 4095) * 997 % (uint64_t)n_rows);
+        if (pattern == 4 && ((h & 255) < 159)) row = (int64_t)(((h >> 8) & 4095) * 997 % (uint64_t)n_rows);
     }
     idx[i] = (int)row;
 }
@@ -173,7 +176,7 @@ void run(EncodeTiled enc, uint8_t* table, int64_t n_rows, int* idx, int64_t n_ch
     CK(cudaFree(dump));
 }
 
-int main() {
+int main(int argc, char**) {
     EncodeTiled enc = nullptr;
     cudaDriverEntryPointQueryResult q;
     CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&enc, cudaEnableDefault, &q));
@@ -195,19 +198,30 @@ int main() {
         const int64_t max_rows = table_bytes / 64;
         CK(cudaMalloc(&idx, (max_rows / 128) * K * 128 * sizeof(int) / 4));       // a quarter of the tiles is plenty
     }
-    for (int pattern = 0; pattern < 3; ++pattern) {
+    const bool quick = argc > 1;              // any argument: only the 16-warp / zero-row-pool follow-up
+    for (int pattern = quick ? 1 : 0; pattern < (quick ? 5 : 3); ++pattern) {
         {
             const int64_t n_rows = table_bytes / 64, n_chunks = (n_rows / 128 / 4) * K;
-            run<64, 1, 8, true>(enc, table, n_rows, idx, n_chunks, K, pattern, h_table);
-            run<64, 4, 4, true>(enc, table, n_rows, idx, n_chunks, K, pattern, h_table);
+            if (!quick) {
+                run<64, 1, 8, true>(enc, table, n_rows, idx, n_chunks, K, pattern, h_table);
+                run<64, 4, 4, true>(enc, table, n_rows, idx, n_chunks, K, pattern, h_table);
+            }
             run<64, 8, 2, true>(enc, table, n_rows, idx, n_chunks, K, pattern, h_table);
-            run<64, 4, 4, false>(enc, table, n_rows, idx, n_chunks, K, pattern, h_table);
+            if (quick) {
+                run<64, 16, 1, true>(enc, table, n_rows, idx, n_chunks, K, pattern, h_table);
+                run<64, 24, 1, true>(enc, table, n_rows, idx, n_chunks, K, pattern, h_table);
+            }
+            if (!quick) run<64, 4, 4, false>(enc, table, n_rows, idx, n_chunks, K, pattern, h_table);
             run<64, 8, 2, false>(enc, table, n_rows, idx, n_chunks, K, pattern, h_table);
         }
         {
             const int64_t n_rows = table_bytes / 128, n_chunks = (n_rows / 128 / 2) * K;
-            run<128, 1, 8, true>(enc, table, n_rows, idx, n_chunks, K, pattern, h_table);
+            if (!quick) run<128, 1, 8, true>(enc, table, n_rows, idx, n_chunks, K, pattern, h_table);
             run<128, 4, 3, true>(enc, table, n_rows, idx, n_chunks, K, pattern, h_table);
+            if (quick) {
+                run<128, 8, 1, true>(enc, table, n_rows, idx, n_chunks, K, pattern, h_table);
+                run<128, 12, 1, true>(enc, table, n_rows, idx, n_chunks, K, pattern, h_table);
+            }
             run<128, 4, 3, false>(enc, table, n_rows, idx, n_chunks, K, pattern, h_table);
         }
     }

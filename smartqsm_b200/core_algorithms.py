@@ -119,6 +119,13 @@ class SpconvBasedContraction(CoreAlgorithmBase):
         self.history: List[dict] = []
 
     def input(self, **kwargs) -> None:
+        pts = kwargs.get("points")
+        if pts is not None and hasattr(pts, "global_shift") and hasattr(pts, "scale"):
+            # a PreparedCloud: `skeletonization.run(points=prepared)` keeps the device-resident hand-over of
+            # prepare_input(); one made on another engine is scaled on the host like the reference does (:922)
+            if self._prepared and pts.engine is self._engine:
+                return
+            kwargs = dict(kwargs, points=pts.points * pts.scale)
         super().input(**kwargs)
         if "points" in kwargs:
             self._loaded = False

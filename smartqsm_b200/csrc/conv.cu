@@ -325,6 +325,12 @@ __global__ void __launch_bounds__(256) k_heads(const float* __restrict__ feat, c
 
 std::vector<float> make_tc_weight_image(const float* w_kcico, int kv, int ci, int co);   // conv_tc.cu
 std::vector<float> make_tc_weight_image_f16(const float* w_kcico, int kv, int ci, int co);
+std::vector<float> make_tma_weight_image(const float* w_kcico, int kv, int ci, int co, int cs, int g);   // conv_tma.cu
+bool conv_tma_supported(int ci, int co, int kv, bool cat);
+int tma_group(int cs, int kv);
+void act_split_rows(Ctx& cx, const float* in, const float* bn, int c, int bn_off, int bn_stride, int64_t n, void* out, int* range_flag);
+bool conv_tma(Ctx& cx, int ci, int co, int kv, bool cat, const void* splitA, const void* splitB, const int32_t* nbr, const float* wimg,
+              const float* res, const float* sel_src, const uint8_t* sel_flag, float* out, int64_t n_out, int64_t n_in);
 
 static const std::vector<float>& need(const std::map<std::string, std::vector<float>>& st, const std::string& k,
                                       size_t n) {
@@ -351,10 +357,10 @@ static void fold_bn(const std::map<std::string, std::vector<float>>& st, const s
 
 void net_upload(Ctx& cx, NetWeights& nw, const std::map<std::string, std::vector<float>>& st, bool down_flip) {
     std::vector<float> blob;
-    struct Pending { std::string name; size_t w_off, bn_off, img_off, img16_off; bool has_bn, has_img; int ci, co, kv; };
+    struct Pending { std::string name; size_t w_off, bn_off, img_off, img16_off; bool has_bn, has_img; int ci, co, kv; size_t tma_off = 0; bool has_tma = false; };
     std::vector<Pending> pend;
     auto add_conv = [&](const std::string& name, const std::string& wkey, const std::string& bnkey, int ci, int co, int kv,
-                        int ci_pad, bool flip) {
+                        int ci_pad, bool flip, bool cat = false) {
         const auto& W = need(st, wkey, (size_t)co * kv * ci);   // [co][k][ci]
         Pending p{name, blob.size(), 0, 0, 0, !bnkey.empty(), false, ci_pad, co, kv};
         blob.resize(blob.size() + (size_t)kv * ci_pad * co, 0.0f);
@@ -381,6 +387,14 @@ void net_upload(Ctx& cx, NetWeights& nw, const std::map<std::string, std::vector
             p.img16_off = blob.size();
             blob.insert(blob.end(), img16.begin(), img16.end());
         }
+        if (conv_tma_supported(ci_pad, co, kv, cat)) {           // TMA-gather weight image (conv_tma.cu)
+            const int cs = cat ? ci_pad / 2 : ci_pad;
+            std::vector<float> img = make_tma_weight_image(&blob[p.w_off], kv, ci_pad, co, cs, tma_group(cs, kv));
+            while (blob.size() % 64) blob.push_back(0.0f);
+            p.tma_off = blob.size();
+            p.has_tma = true;
+            blob.insert(blob.end(), img.begin(), img.end());
+        }
         pend.push_back(p);
     };
     add_conv("input", "input_conv.0.weight", "", 3, kPlanes[0], 27, 4, false);
@@ -394,8 +408,8 @@ void net_upload(Ctx& cx, NetWeights& nw, const std::map<std::string, std::vector
             int cn = kPlanes[l + 1];
             add_conv(L + ".down", prefix + ".conv.2.weight", prefix + ".conv.0", c, cn, 8, c, down_flip);
             add_conv(L + ".up", prefix + ".deconv.2.weight", prefix + ".deconv.0", cn, c, 8, cn, down_flip);
-            add_conv(L + ".tail.i", prefix + ".blocks_tail.block0.i_branch.0.weight", "", 2 * c, c, 1, 2 * c, false);
-            add_conv(L + ".tail.a", prefix + ".blocks_tail.block0.conv_branch.2.weight", prefix + ".blocks_tail.block0.conv_branch.0", 2 * c, c, 27, 2 * c, false);
+            add_conv(L + ".tail.i", prefix + ".blocks_tail.block0.i_branch.0.weight", "", 2 * c, c, 1, 2 * c, false, true);
+            add_conv(L + ".tail.a", prefix + ".blocks_tail.block0.conv_branch.2.weight", prefix + ".blocks_tail.block0.conv_branch.0", 2 * c, c, 27, 2 * c, false, true);
             add_conv(L + ".tail.b", prefix + ".blocks_tail.block0.conv_branch.5.weight", prefix + ".blocks_tail.block0.conv_branch.3", c, c, 27, c, false);
         }
         prefix += ".u";
@@ -413,6 +427,7 @@ void net_upload(Ctx& cx, NetWeights& nw, const std::map<std::string, std::vector
         c.bn = p.has_bn ? nw.blob.p + p.bn_off : nullptr;
         c.wimg = p.has_img ? nw.blob.p + p.img_off : nullptr;
         c.wimg16 = p.has_img ? nw.blob.p + p.img16_off : nullptr;
+        c.wimg_tma = p.has_tma ? nw.blob.p + p.tma_off : nullptr;
         nw.conv[p.name] = c;
     }
     // heads (App. A #48-51)
@@ -483,9 +498,29 @@ static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, boo
     snprintf(fam, sizeof(fam), "conv_%s_ci%d_co%d_k%d", use_tc ? "tc" : "ffma", w.ci, w.co, w.kv);
     const double alg_bytes = 4.0 * ((double)n_in * w.ci + (double)n_out * w.co) + 4.0 * (nbr ? (double)w.kv * n_out : 0.0) +
                              (res ? 4.0 * (double)n_out * w.co : 0.0);
+    static const char* tma_only = getenv("SQSM_TMA_ONLY");        // debug: restrict the TMA kernel to layers whose name contains this
+    if (use_tc && nw.mode == 4 && w.wimg_tma && conv_tma_supported(w.ci, w.co, w.kv, cat) &&
+        (!tma_only || name.find(tma_only) != std::string::npos)) {
+        // activation + FP16 hi/lo split into "split rows", then the TMA-gather tensor-core kernel
+        const int ca = cat ? w.ci / 2 : w.ci;
+        const int64_t halves = (n_in + kTmZeroRows) * 2 * ca;
+        DBuf<float> sa((halves + 1) / 2, cx.st), sb;
+        {
+            ProfScope pa(cx, "act_split", (double)n_in * w.ci * 8.0, 0.0);
+            act_split_rows(cx, inA, w.bn, ca, 0, w.ci, n_in, sa.p, nw.range_flag);
+            if (cat) {
+                sb.alloc((halves + 1) / 2, cx.st);
+                act_split_rows(cx, inB, w.bn, ca, ca, w.ci, n_in, sb.p, nw.range_flag);
+            }
+        }
+        snprintf(fam, sizeof(fam), "conv_tma_ci%d_co%d_k%d", w.ci, w.co, w.kv);
+        ProfScope ps(cx, fam, alg_bytes, 0.0);
+        if (conv_tma(cx, w.ci, w.co, w.kv, cat, sa.p, sb.p, nbr, w.wimg_tma, res, sel_src, sel_flag, out, n_out, n_in)) return;
+        throw CudaError("conv_tma: unsupported shape for layer " + name);
+    }
     if (use_tc) {
         // activation + TF32 hi/lo split once per element, then the tensor-core implicit GEMM
-        const bool f16 = nw.mode == 3;
+        const bool f16 = nw.mode == 3 || nw.mode == 4;
         const bool precise = nw.mode == 1 || f16;
         const int ca = cat ? w.ci / 2 : w.ci;
         // FP16 operands take half the space of TF32 ones: allocate in float units either way

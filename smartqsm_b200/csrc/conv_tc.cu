@@ -24,103 +24,11 @@
 // TMA is not used for A: the rows of a tile come from arbitrary addresses (a gather), which is exactly
 // what TMA cannot express; the weight chunk is small and shared by all tiles (L2 resident).
 #include "engine.h"
+#include "tc_ptx.cuh"
 #include <cuda_fp16.h>
 #include <cstring>
 
 namespace sqsm {
-
-// ------------------------------------------------------------------------------------------ PTX wrappers
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_slot, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-
-// D[tmem] (+)= A[smem desc] . B[smem desc], kind::tf32, issued by ONE thread for the CTA
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// kind::f16 variant (FP16 operands, FP32 accumulation in TMEM); K = 16 elements = 32 bytes per instruction
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// mbarrier arrives when all previously issued MMAs of this thread have completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// 32 lanes x 16 consecutive 32-bit columns of TMEM -> 16 registers per thread
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// 16-byte asynchronous global->shared copy; src_bytes = 0 writes zeros (absent neighbour)
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-// the mbarrier receives one arrival from this thread once all its prior cp.async have landed
-__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// round-to-nearest TF32 (low 13 mantissa bits cleared).  Rounding (not truncating) both the "hi" part and the
-// remainder keeps the 3xTF32 error unbiased, so it grows like sqrt(K) instead of K.
-__device__ __forceinline__ float tf32_rn(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100 version 1):
-// rows of 128 B, groups of 8 rows 1024 B apart (SBO), LBO unused (1), 16-byte chunks XOR-swizzled by row&7.
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
 
 // ------------------------------------------------------------------------------------------ kernel
 
@@ -147,7 +55,7 @@ constexpr int kTcProducers = 128;     // threads per producer group; thread t ow
 constexpr int kTcProdWarps = kTcGroups * 4;
 constexpr int kTcEpilogue = 128;      // next 4 warps: TMEM -> registers -> global; thread owns one tile row
 constexpr int kTcThreads = kTcGroups * kTcProducers + kTcEpilogue + 32;   // last warp: MMA issuer
-constexpr uint32_t kTmemCols = 128;   // two accumulator stages of 64 columns
+constexpr uint32_t kTmemCols = 256;   // two accumulator stages of up to 128 columns ([hi*hi + lo*hi | hi*lo] when PRECISE)
 
 __host__ __device__ constexpr int tc_stages(int np) {
     int fit = (227 * 1024 - 2048) / (2 * 128 * 128 + 2 * np * 128);
@@ -172,6 +80,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
     constexpr int kTcStages = tc_stages(NP);
     constexpr uint32_t FMT = F16 ? 0u : 2u;           // a/b format: F16 = 0, TF32 = 2 (UMMA::F16F32Format)
     constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // PRECISE: the hi and lo weight tiles are adjacent in shared memory ([NP rows][128 B] each), so ONE instruction with
+    // N = 2*NP computes A_hi.[W_hi | W_lo] into two accumulator halves and a second one adds A_lo.W_hi to the first half:
+    // two MMAs and two reads of the A tile per K step instead of three (the tiny-N MMAs are bound by the A-tile fetch)
+    constexpr uint32_t IDESC2 = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)((2 * NP) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t ACC = PRECISE ? 2 * NP : NP;   // TMEM columns of one accumulator stage
     static_assert(CI % 8 == 0 && NP <= 64 && B_BYTES % 1024 == 0, "tile shape");
 
     extern __shared__ uint8_t smem_raw[];
@@ -289,24 +202,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
             const bool live = row < a.n_out;
             mbar_wait(tfull0 + 8 * as, aph);
             tc_fence_after();
-            float acc[NP];
-            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + as * 64u;
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + as * ACC;
+            const size_t o = (size_t)row * CO;
+            const bool take_src = live && a.sel_flag && a.sel_flag[row] == 0;
             #pragma unroll
-            for (int c = 0; c < NP; c += 16) tmem_ld16(taddr + c, acc + c);
-            tc_fence_before();
-            mbar_arrive(tempty0 + 8 * as);              // this accumulator stage may be overwritten
-            if (live) {
-                const size_t o = (size_t)row * CO;
-                const bool take_src = a.sel_flag && a.sel_flag[row] == 0;
-                #pragma unroll
-                for (int c = 0; c < CO; c += 4) {
-                    float4 r = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
-                    if (a.res) {
-                        float4 e = *reinterpret_cast<const float4*>(a.res + o + c);
-                        r.x += e.x; r.y += e.y; r.z += e.z; r.w += e.w;
+            for (int c0 = 0; c0 < NP; c0 += 16) {           // 16 output channels at a time
+                float v[16];
+                tmem_ld16(taddr + c0, v);
+                if (PRECISE) {
+                    float w[16];
+                    tmem_ld16(taddr + NP + c0, w);
+                    #pragma unroll
+                    for (int c = 0; c < 16; ++c) v[c] += w[c];
+                }
+                if (c0 + 16 >= NP) {
+                    tc_fence_before();
+                    mbar_arrive(tempty0 + 8 * as);          // all columns read: this accumulator stage may be overwritten
+                }
+                if (live && c0 < CO) {
+                    #pragma unroll
+                    for (int c = 0; c < 16; c += 4) {
+                        float4 r = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                        if (a.res) {
+                            float4 e = *reinterpret_cast<const float4*>(a.res + o + c0 + c);
+                            r.x += e.x; r.y += e.y; r.z += e.z; r.w += e.w;
+                        }
+                        if (take_src) r = *reinterpret_cast<const float4*>(a.sel_src + o + c0 + c);
+                        *reinterpret_cast<float4*>(a.out + o + c0 + c) = r;
                     }
-                    if (take_src) r = *reinterpret_cast<const float4*>(a.sel_src + o + c);
-                    *reinterpret_cast<float4*>(a.out + o + c) = r;
                 }
             }
         }
@@ -317,7 +240,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
             const uint32_t as = tile_it & 1u, aph = (tile_it >> 1) & 1u;
             mbar_wait(tempty0 + 8 * as, aph ^ 1u);      // epilogue has drained this accumulator stage
             tc_fence_after();
-            const uint32_t tmem_d = tmem_base + as * 64u;
+            const uint32_t tmem_d = tmem_base + as * ACC;
             #pragma unroll 1
             for (int j = 0; j < NCH; ++j, ++it) {
                 const uint32_t stage = it % kTcStages, ph = (it / kTcStages) & 1u;
@@ -329,12 +252,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
                 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {        // 4 K steps of 8 tf32 (32 B) inside the 128 B swizzle span
                     const uint64_t ah = make_desc_sw128(sA_hi + ks * 32), bh = make_desc_sw128(sB_hi + ks * 32);
-                    if (F16) umma_f16(tmem_d, ah, bh, IDESC, (j | ks) ? 1u : 0u);
-                    else umma_tf32(tmem_d, ah, bh, IDESC, (j | ks) ? 1u : 0u);
                     if (PRECISE) {
-                        const uint64_t al = make_desc_sw128(sA_lo + ks * 32), bl = make_desc_sw128(sB_lo + ks * 32);
-                        if (F16) { umma_f16(tmem_d, al, bh, IDESC, 1u); umma_f16(tmem_d, ah, bl, IDESC, 1u); }
-                        else { umma_tf32(tmem_d, al, bh, IDESC, 1u); umma_tf32(tmem_d, ah, bl, IDESC, 1u); }
+                        const uint64_t al = make_desc_sw128(sA_lo + ks * 32);
+                        if (F16) { umma_f16(tmem_d, ah, bh, IDESC2, (j | ks) ? 1u : 0u); umma_f16(tmem_d, al, bh, IDESC, 1u); }
+                        else { umma_tf32(tmem_d, ah, bh, IDESC2, (j | ks) ? 1u : 0u); umma_tf32(tmem_d, al, bh, IDESC, 1u); }
+                    } else {
+                        if (F16) umma_f16(tmem_d, ah, bh, IDESC, (j | ks) ? 1u : 0u);
+                        else umma_tf32(tmem_d, ah, bh, IDESC, (j | ks) ? 1u : 0u);
                     }
                 }
                 umma_commit(empty0 + 8 * stage);       // stage reusable once these MMAs have read it

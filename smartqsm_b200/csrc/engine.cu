@@ -131,8 +131,8 @@ extern "C" int sqsm_finalize_weights(sqsm_handle h) {
     net_upload(h->cx, h->nw, h->state, h->cfg.down_kernel_flip != 0);
     int mode = h->cfg.conv_mode;
     if (mode == 0) { const char* env = getenv("SQSM_CONV_MODE"); mode = env ? atoi(env) : 4; }
-    SQSM_CHECK(mode >= 1 && mode <= 4, "conv_mode must be 0..4");
-    h->nw.mode = mode - 1;                                   // 0 FFMA, 1 3xTF32, 2 TF32, 3 3xFP16
+    SQSM_CHECK(mode >= 1 && mode <= 5, "conv_mode must be 0..5");
+    h->nw.mode = mode - 1;                                   // 0 FFMA, 1 3xTF32, 2 TF32, 3 3xFP16, 4 3xFP16 + TMA gather
     if (const char* env = getenv("SQSM_TC_MIN_CO")) h->nw.tc_min_co = atoi(env);
     SQSM_API_END(h)
 }

@@ -55,6 +55,7 @@ struct ConvW {                          // one convolution, device resident
     float* bn = nullptr;                // [2][ci] alpha, beta of the BatchNorm+ReLU in FRONT of the conv (or null)
     float* wimg = nullptr;              // tensor-core weight image, TF32 hi/lo (conv_tc.cu) or null
     float* wimg16 = nullptr;            // tensor-core weight image, FP16 hi/lo
+    float* wimg_tma = nullptr;          // weight image of the TMA-gather kernel (conv_tma.cu) or null
 };
 
 struct HeadW {                          // output_layer BN + both MLP heads; index 0 = offset, 1 = regression
@@ -70,12 +71,15 @@ struct NetWeights {
     HeadW head;
     bool ready = false;
     int mode = 3;                       // 0 = fp32 FFMA everywhere, 1 = tcgen05 3xTF32 (fp32-class), 2 = tcgen05 single-pass TF32,
-                                        // 3 = tcgen05 3xFP16 (2-term FP16 split, fp32-class, half the operand bytes)
+                                        // 3 = tcgen05 3xFP16 (2-term FP16 split, fp32-class, half the operand bytes),
+                                        // 4 = 3xFP16 with the TMA gather4 kernel where it covers the shape (else as 3)
     int* range_flag = nullptr;          // device flag: an activation left the FP16 range in mode 3
     int tc_min_co = 16;                 // layers with at least this many output channels use the tensor-core kernel
                                         // (measured: with FP16 operands the tcgen05 kernel wins from C=16 up; with TF32
                                         // operands only from C=32)
 };
+
+constexpr int kTmZeroRows = 1024;        // rows of zeros behind every split-row array (absent neighbours, conv_tma.cu)
 
 struct Net;                             // conv.cu
 

@@ -90,6 +90,7 @@ def test_prepare_input_on_the_plugin_equals_host_round_trip():
                using_density_adaptation_in_skeletonization=True)
     a = SpconvBasedContraction(**kw)
     prepared = a.prepare_input(raw, **cfg)
+    a.input(points=prepared)                                                   # what `skeletonization.run(points=prepared)` does
     for thunk in a.get_pipeline():
         thunk()
     b = SpconvBasedContraction(**kw)
