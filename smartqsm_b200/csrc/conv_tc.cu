@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
                 }
                 if (live && c0 < CO) {
                     #pragma unroll
-                    for (int c = 0; c < 16; c += 4) {
+                    for (int c = 0; c < 16 && c0 + c < CO; c += 4) {      // CO may be 8 (NP padded to 16)
                         float4 r = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
                         if (a.res) {
                             float4 e = *reinterpret_cast<const float4*>(a.res + o + c0 + c);
