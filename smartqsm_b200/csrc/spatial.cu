@@ -318,31 +318,46 @@ __global__ void __launch_bounds__(256) k_nn_sqdist_pairs(const Brick* __restrict
             __syncwarp();
             best = __longlong_as_double((long long)S.best[lane]);
         }
-        if (valid && best > edge * edge) {                                         // exact ring fallback (rare)
-            ++fb;
-            const double qx = meanA[3 * r], qy = meanA[3 * r + 1], qz = meanA[3 * r + 2];
-            const uint64_t key = A[a].key;
+        // exact ring fallback (a few queries per thousand): the warp serves its unsettled queries one at a time, the 32 lanes
+        // sharing the bricks of every ring (hash probes) instead of one lane probing alone while 31 wait
+        unsigned need = __ballot_sync(0xFFFFFFFFu, valid && best > edge * edge);
+        fb += (need >> lane) & 1u;
+        while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const int64_t rq = base + src;
+            const double qx = meanA[3 * rq], qy = meanA[3 * rq + 1], qz = meanA[3 * rq + 2];
+            const uint64_t key = A[__shfl_sync(0xFFFFFFFFu, a, src)].key;
             const int bz = (int)key_z(key), by = (int)key_y(key), bx = (int)key_x(key);
+            double bq = __shfl_sync(0xFFFFFFFFu, best, src);
             int ring = 1;
-            while (best > (double)ring * edge * (double)ring * edge && ring < max_ring) {
+            while (bq > (double)ring * edge * (double)ring * edge && ring < max_ring) {
                 ++ring;
-                for (int dz = -ring; dz <= ring; ++dz)
-                    for (int dy = -ring; dy <= ring; ++dy) {
-                        const bool shell = (abs(dz) == ring) || (abs(dy) == ring);
-                        for (int dx = -ring; dx <= ring; dx += (shell ? 1 : 2 * ring)) {
-                            int z = bz + dz, y = by + dy, x = bx + dx;
-                            if (z < 0 || y < 0 || x < 0 || z > 65535 || y > 65535 || x > 65535) continue;
-                            int id = hash_find(hB, pack_key(0u, (uint32_t)z, (uint32_t)y, (uint32_t)x));
-                            if (id < 0) continue;
-                            const int cb = B[id].base, cn = B[id].count;
-                            for (int i = 0; i < cn; ++i) {
-                                double ex = qx - meanB[3 * (size_t)(cb + i)], ey = qy - meanB[3 * (size_t)(cb + i) + 1],
-                                       ez = qz - meanB[3 * (size_t)(cb + i) + 2];
-                                best = fmin(best, ex * ex + ey * ey + ez * ez);
-                            }
+                const int side = 2 * ring + 1;
+                double mine = bq;
+                for (int t = lane; t < side * side; t += 32) {
+                    const int dz = t / side - ring, dy = t % side - ring;
+                    const bool shell = (abs(dz) == ring) || (abs(dy) == ring);
+                    const int z = bz + dz, y = by + dy;
+                    if (z < 0 || y < 0 || z > 65535 || y > 65535) continue;
+                    for (int dx = -ring; dx <= ring; dx += (shell ? 1 : 2 * ring)) {
+                        const int x = bx + dx;
+                        if (x < 0 || x > 65535) continue;
+                        const int id = hash_find(hB, pack_key(0u, (uint32_t)z, (uint32_t)y, (uint32_t)x));
+                        if (id < 0) continue;
+                        const int cb = B[id].base, cn = B[id].count;
+                        for (int i = 0; i < cn; ++i) {
+                            const double ex = qx - meanB[3 * (size_t)(cb + i)], ey = qy - meanB[3 * (size_t)(cb + i) + 1],
+                                         ez = qz - meanB[3 * (size_t)(cb + i) + 2];
+                            mine = fmin(mine, ex * ex + ey * ey + ez * ez);
                         }
                     }
+                }
+                #pragma unroll
+                for (int d = 16; d > 0; d >>= 1) mine = fmin(mine, __shfl_xor_sync(0xFFFFFFFFu, mine, d));
+                bq = mine;
             }
+            if (lane == src) best = bq;
         }
         if (valid) local_sum += best;
     }
