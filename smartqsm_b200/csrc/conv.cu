@@ -462,7 +462,8 @@ static void conv_dispatch(Ctx& cx, const ConvArgs& a) {
 // conv_tc.cu
 bool conv_tc(Ctx& cx, int ci, int co, int kv, bool cat, const float* inA, const float* inB, const float* inA_lo,
              const float* inB_lo, const int32_t* nbr, const float* wimg, const float* res, const float* sel_src,
-             const uint8_t* sel_flag, float* out, int64_t n_out, bool precise, bool f16);
+             const uint8_t* sel_flag, float* out, int64_t n_out, bool precise, bool f16, void* out_hi = nullptr,
+             void* out_lo = nullptr, const float* out_bn = nullptr, int* range_flag = nullptr);
 void act_split(Ctx& cx, const float* in, const float* bn, int c, int bn_off, int bn_stride, int64_t n, float* hi, float* lo);
 void act_split_f16(Ctx& cx, const float* in, const float* bn, int c, int bn_off, int bn_stride, int64_t n, void* hi, void* lo,
                    int* range_flag);
@@ -487,10 +488,22 @@ static bool conv_ffma(Ctx& cx, const ConvW& w, bool cat, const ConvArgs& a) {
 }
 
 // One convolution of the network: tensor-core path for C_out >= 16 (inputs pre-activated once), FFMA otherwise.
+// Activation split handed from the convolution that produces a tensor to its ONE consumer: the producer's epilogue applies
+// the consumer's BatchNorm + ReLU and writes the FP16 hi / lo operands itself (conv_tc.cu), so the separate k_act_split_f16
+// pass and - when nothing else reads the tensor - its float32 round trip disappear.
+struct FusedSplit {
+    DBuf<float> hi, lo;
+    bool ready = false;
+};
+
+static bool tc_f16_layer(const NetWeights& nw, const ConvW& w) { return nw.mode == 3 && w.wimg16 && w.co >= nw.tc_min_co; }
+
 static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, bool cat, const float* inA, const float* inB,
                      const int32_t* nbr, float* out, int64_t n_out, int64_t n_in, const float* res = nullptr,
-                     const float* sel_src = nullptr, const uint8_t* sel_flag = nullptr) {
+                     const float* sel_src = nullptr, const uint8_t* sel_flag = nullptr, const FusedSplit* consume = nullptr,
+                     FusedSplit* produce = nullptr, const char* consumer = nullptr, bool need_fp32 = true) {
     const ConvW& w = nw.conv.at(name);
+    if (produce) produce->ready = false;
     if (n_out <= 0) return;
     const bool use_tc = nw.mode != 0 && w.wimg && w.co >= nw.tc_min_co;
     // per-kernel scope: algorithmic bytes of SURVEY 8(d): features in + out, rulebook entries, residual re-read
@@ -525,9 +538,14 @@ static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, boo
         const int ca = cat ? w.ci / 2 : w.ci;
         // FP16 operands take half the space of TF32 ones: allocate in float units either way
         const int64_t elems = f16 ? (n_in * ca + 1) / 2 : n_in * ca;
-        DBuf<float> a_hi(elems, cx.st), a_lo, b_hi, b_lo;
-        if (precise) a_lo.alloc(elems, cx.st);
-        {
+        DBuf<float> a_hi, a_lo, b_hi, b_lo;
+        const float *pa_hi, *pa_lo;
+        if (consume && consume->ready && f16 && !cat) {          // the producer already wrote this layer's operands
+            pa_hi = consume->hi.p;
+            pa_lo = consume->lo.p;
+        } else {
+            a_hi.alloc(elems, cx.st);
+            if (precise) a_lo.alloc(elems, cx.st);
             ProfScope pa(cx, "act_split", (double)n_in * w.ci * (f16 ? 8.0 : 4.0 * (precise ? 3 : 2)), 0.0);
             if (f16) act_split_f16(cx, inA, w.bn, ca, 0, w.ci, n_in, a_hi.p, a_lo.p, nw.range_flag);
             else act_split(cx, inA, w.bn, ca, 0, w.ci, n_in, a_hi.p, a_lo.p);
@@ -537,11 +555,28 @@ static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, boo
                 if (f16) act_split_f16(cx, inB, w.bn, ca, ca, w.ci, n_in, b_hi.p, b_lo.p, nw.range_flag);
                 else act_split(cx, inB, w.bn, ca, ca, w.ci, n_in, b_hi.p, b_lo.p);
             }
+            pa_hi = a_hi.p;
+            pa_lo = a_lo.p;
         }
+        // fused split for the consumer: only between two FP16 tensor-core layers, and the consumer must own a BatchNorm
+        void *o_hi = nullptr, *o_lo = nullptr;
+        const float* o_bn = nullptr;
+        if (produce && consumer && f16 && nw.mode == 3) {
+            const ConvW& wc = nw.conv.at(consumer);
+            if (tc_f16_layer(nw, wc) && wc.bn && wc.ci == w.co) {
+                const int64_t oe = (n_out * w.co + 1) / 2;
+                produce->hi.alloc(oe, cx.st);
+                produce->lo.alloc(oe, cx.st);
+                produce->ready = true;
+                o_hi = produce->hi.p; o_lo = produce->lo.p; o_bn = wc.bn;
+            }
+        }
+        float* o_f32 = (o_hi && !need_fp32) ? nullptr : out;
         ProfScope ps(cx, fam, alg_bytes, 0.0);
-        if (conv_tc(cx, w.ci, w.co, w.kv, cat, a_hi.p, b_hi.p, a_lo.p, b_lo.p, nbr, f16 ? w.wimg16 : w.wimg, res, sel_src, sel_flag,
-                    out, n_out, precise, f16))
+        if (conv_tc(cx, w.ci, w.co, w.kv, cat, pa_hi, b_hi.p, pa_lo, b_lo.p, nbr, f16 ? w.wimg16 : w.wimg, res, sel_src, sel_flag,
+                    o_f32, n_out, precise, f16, o_hi, o_lo, o_bn, nw.range_flag))
             return;
+        if (produce) produce->ready = false;
     }
     ProfScope ps(cx, fam, alg_bytes, 0.0);
     ConvArgs ar;
@@ -584,14 +619,19 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
         {   // ResidualBlock with identity i_branch (sparse_module.py:32-39): out = convB(bnrelu(convA(bnrelu(x)))) + x
             ProfScope pt(cx, lvl_family(l), 2.0 * (4.0 * n * c * 2 + 4.0 * 27 * n) + 4.0 * n * c,
                          2.0 * 2.0 * (double)lv[l].pairs * c * c);
-            conv_any(cx, nw, L + ".blk.a", false, cur_in.p, nullptr, lv[l].nbr.p, tmp[l].p, n, n);
-            conv_any(cx, nw, L + ".blk.b", false, tmp[l].p, nullptr, lv[l].nbr.p, enc[l].p, n, n, cur_in.p);
+            FusedSplit sp_mid;                                  // bnrelu(convA(.)) as convB's operands, written by convA
+            const std::string nb = L + ".blk.b";
+            conv_any(cx, nw, L + ".blk.a", false, cur_in.p, nullptr, lv[l].nbr.p, tmp[l].p, n, n, nullptr, nullptr, nullptr, nullptr,
+                     &sp_mid, nb.c_str(), /*need_fp32=*/false);
+            conv_any(cx, nw, nb, false, tmp[l].p, nullptr, lv[l].nbr.p, enc[l].p, n, n, cur_in.p, nullptr, nullptr, &sp_mid);
         }
         if (keep) keep_copy(cx, fb, "enc" + std::to_string(l), enc[l].p, n, c, l);
         if (l + 1 < n_levels) {
             const int64_t nn = lv[l + 1].n;
             DBuf<float> nxt(nn * kPlanes[l + 1], st);
             ProfScope pt(cx, "down_up", 4.0 * (n * c + nn * kPlanes[l + 1]) + 4.0 * n, 2.0 * (double)n * c * kPlanes[l + 1]);
+            // (no fused split here: the k = 8 down convolution is epilogue bound, the extra stores cost more than the
+            // separate split pass - measured 9.8 -> 21 ms per C3 step for 16 -> 32)
             conv_any(cx, nw, L + ".down", false, enc[l].p, nullptr, lv[l].child.p, nxt.p, nn, n);
             cur_in = std::move(nxt);
         }
@@ -615,9 +655,11 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
             ProfScope pt(cx, lvl_family(l), 4.0 * n * (2 * c + c) * 2 + 4.0 * n * (c + c) + 2.0 * 4.0 * 27 * n + 4.0 * n * c,
                          2.0 * (double)lv[l].pairs * (2 * c * c + c * c) + 2.0 * (double)n * 2 * c * c);
             conv_any(cx, nw, L + ".tail.i", true, enc[l].p, up.p, nullptr, res.p, n, n);
-            conv_any(cx, nw, L + ".tail.a", true, enc[l].p, up.p, lv[l].nbr.p, tmp[l].p, n, n);
-            conv_any(cx, nw, L + ".tail.b", false, tmp[l].p, nullptr, lv[l].nbr.p, out.p, n, n, res.p, enc[l].p,
-                     lv[l].row_desc.p);
+            FusedSplit sp_mid;
+            const std::string nb = L + ".tail.b";
+            conv_any(cx, nw, L + ".tail.a", true, enc[l].p, up.p, lv[l].nbr.p, tmp[l].p, n, n, nullptr, nullptr, nullptr, nullptr,
+                     &sp_mid, nb.c_str(), /*need_fp32=*/false);
+            conv_any(cx, nw, nb, false, tmp[l].p, nullptr, lv[l].nbr.p, out.p, n, n, res.p, enc[l].p, lv[l].row_desc.p, &sp_mid);
         }
         if (keep) keep_copy(cx, fb, "dec" + std::to_string(l), out.p, n, c, l);
         cur = std::move(out);

@@ -42,7 +42,12 @@ struct TcArgs {
     const float* res;         // [n_out][CO] or nullptr
     const float* sel_src;     // [n_out][CO] or nullptr
     const uint8_t* sel_flag;
-    float* out;               // [n_out][CO]
+    float* out;               // [n_out][CO], or nullptr when only the fused split below is wanted
+    // fused activation split for the one consumer of this output (F16 kernels): hi/lo = split(relu(out * alpha + beta))
+    __half* out_hi;           // [n_out][CO] or nullptr
+    __half* out_lo;
+    const float* out_bn;      // alpha[CO] then beta[CO] of the consumer's BatchNorm
+    int* range_flag;
     int n_out;
     int n_tiles;
 };
@@ -221,14 +226,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant
                 }
                 if (live && c0 < CO) {
                     #pragma unroll
-                    for (int c = 0; c < 16 && c0 + c < CO; c += 4) {      // CO may be 8 (NP padded to 16)
-                        float4 r = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                    for (int c = 0; c < 16 && c0 + c < CO; c += 8) {      // CO may be 8 (NP padded to 16)
+                        float r[8];
+                        #pragma unroll
+                        for (int i = 0; i < 8; ++i) r[i] = v[c + i];
                         if (a.res) {
-                            float4 e = *reinterpret_cast<const float4*>(a.res + o + c0 + c);
-                            r.x += e.x; r.y += e.y; r.z += e.z; r.w += e.w;
+                            const float4 e0 = *reinterpret_cast<const float4*>(a.res + o + c0 + c);
+                            const float4 e1 = *reinterpret_cast<const float4*>(a.res + o + c0 + c + 4);
+                            r[0] += e0.x; r[1] += e0.y; r[2] += e0.z; r[3] += e0.w;
+                            r[4] += e1.x; r[5] += e1.y; r[6] += e1.z; r[7] += e1.w;
                         }
-                        if (take_src) r = *reinterpret_cast<const float4*>(a.sel_src + o + c0 + c);
-                        *reinterpret_cast<float4*>(a.out + o + c0 + c) = r;
+                        if (take_src) {
+                            const float4 e0 = *reinterpret_cast<const float4*>(a.sel_src + o + c0 + c);
+                            const float4 e1 = *reinterpret_cast<const float4*>(a.sel_src + o + c0 + c + 4);
+                            r[0] = e0.x; r[1] = e0.y; r[2] = e0.z; r[3] = e0.w;
+                            r[4] = e1.x; r[5] = e1.y; r[6] = e1.z; r[7] = e1.w;
+                        }
+                        if (a.out) {
+                            *reinterpret_cast<float4*>(a.out + o + c0 + c) = make_float4(r[0], r[1], r[2], r[3]);
+                            *reinterpret_cast<float4*>(a.out + o + c0 + c + 4) = make_float4(r[4], r[5], r[6], r[7]);
+                        }
+                        if (F16 && a.out_hi) {               // the consumer's BN + ReLU + FP16 hi/lo split, fused: 16-byte stores
+                            const int ch = c0 + c;
+                            float x[8];
+                            float mx = 0.f;
+                            #pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                x[i] = fmaxf(fmaf(r[i], a.out_bn[ch + i], a.out_bn[CO + ch + i]), 0.f);
+                                mx = fmaxf(mx, x[i]);
+                            }
+                            if (!(mx < 3.0e4f)) *a.range_flag = 1;
+                            uint32_t hw[4], lw[4];
+                            #pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+                                const float2 f = __half22float2(h);
+                                const __half2 l = __floats2half2_rn(x[2 * i] - f.x, x[2 * i + 1] - f.y);
+                                hw[i] = *reinterpret_cast<const uint32_t*>(&h);
+                                lw[i] = *reinterpret_cast<const uint32_t*>(&l);
+                            }
+                            *reinterpret_cast<uint4*>(a.out_hi + o + ch) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                            *reinterpret_cast<uint4*>(a.out_lo + o + ch) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        }
                     }
                 }
             }
@@ -416,8 +455,10 @@ static void launch_tc(Ctx& cx, const TcArgs& a0, bool precise, bool f16) {
 // Dispatch on the shapes that occur in SmartTreeXX. Returns false for shapes it does not cover.
 bool conv_tc(Ctx& cx, int ci, int co, int kv, bool cat, const float* inA, const float* inB, const float* inA_lo,
              const float* inB_lo, const int32_t* nbr, const float* wimg, const float* res, const float* sel_src,
-             const uint8_t* sel_flag, float* out, int64_t n_out, bool precise, bool f16) {
+             const uint8_t* sel_flag, float* out, int64_t n_out, bool precise, bool f16, void* out_hi, void* out_lo,
+             const float* out_bn, int* range_flag) {
     TcArgs a;
+    a.out_hi = (__half*)out_hi; a.out_lo = (__half*)out_lo; a.out_bn = out_bn; a.range_flag = range_flag;
     a.inA = inA; a.inB = inB; a.inA_lo = inA_lo; a.inB_lo = inB_lo; a.nbr = nbr; a.wimg = wimg; a.res = res; a.sel_src = sel_src; a.sel_flag = sel_flag;
     a.out = out; a.n_out = (int)n_out; a.n_tiles = 0;
 #define SQSM_TC_CASE(CI_, CO_, KV_, CAT_)                                         \
