@@ -54,6 +54,19 @@ struct sqsm_engine {
 
 static std::string g_create_error;
 
+// The double a config value meant: SqsmConfig carries voxel_size as float32, the reference passes the YAML's double to
+// Open3D.  The shortest decimal that round-trips the float (<= 9 significant digits) recovers it exactly for every value
+// a config file would hold (0.01, 0.005, 0.0125, ...); a point within ~1e-5 voxel of a cell face would otherwise fall
+// into a different Chamfer voxel than in the reference.
+static double decimal_double(float v) {
+    char buf[64];
+    for (int digits = 1; digits <= 9; ++digits) {
+        snprintf(buf, sizeof(buf), "%.*g", digits, (double)v);
+        if ((float)strtod(buf, nullptr) == v) return strtod(buf, nullptr);
+    }
+    return (double)v;
+}
+
 #define SQSM_API_BEGIN(h)                                                                         \
     if (!(h)) return 1;                                                                           \
     try {                                                                                         \
@@ -449,7 +462,8 @@ static void step_chamfer(sqsm_engine* h, int shard, int n_shards, double sums[2]
         // B_cd of SURVEY 8(d): both clouds read (12 B/point) + voxel means written and read (2 x 24 B/voxel ~ per point)
         Trace tr(cx, "chamfer");
         ProfScope ps(cx, "chamfer", (double)(h->n + h->cand_n) * (12.0 + 2 * 20.0), 0.0);
-        chamfer_partial(cx, h->P.p, h->n, h->candP.p, h->cand_n, (double)h->cfg.voxel_size, shard, n_shards, sums, counts);
+        // the reference hands Open3D the Python float (a double) of the config, e.g. 0.01, not float32(0.01) = 0.00999999977...
+        chamfer_partial(cx, h->P.p, h->n, h->candP.p, h->cand_n, decimal_double(h->cfg.voxel_size), shard, n_shards, sums, counts);
     }
     T.mark();
     SQSM_CUDA(cudaStreamSynchronize(cx.st));

@@ -275,6 +275,31 @@ def test_chamfer_value(leafoff_state, small_tree):
     assert abs(st["chamfer"] - cd) <= 1e-9 * cd        # float64 sums in a different order
 
 
+@pytest.mark.parametrize("n,seed", [(12000, 2), (12000, 3), (30000, 2), (60000, 4)])
+def test_chamfer_voxel_counts_and_sums(leafoff_state, n, seed):
+    """Both directions of the monitor against Open3D's definition restated in float64: the voxel grids must hold the same
+    number of voxels (the edge is the config's double 0.01, not float32(0.01): seeds 2 and 3 at 12 000 points have a point
+    within 1e-5 voxel of a cell face) and the 1-NN sums must agree to rounding."""
+    from scipy.spatial import cKDTree
+    from smartqsm_b200.synthetic import make_tree
+    pts = make_tree(n, seed)
+    eng = make_engine(leafoff_state, monitored_by_chamfer_distance=True)
+    eng.set_points(pts)
+    eng.step_begin(0, 1)
+    eng.step_segment()
+    sums, counts = eng.step_chamfer(0, 1)
+    eng.step_finish(True, sums[0] / counts[0] + sums[1] / counts[1])
+    Pg, _ = eng.result()
+    P, Q = pts.astype(np.float32).astype(np.float64), Pg.astype(np.float64)
+    mn = np.minimum(P.min(0), Q.min(0))
+    Pv, _ = OC.voxel_trace(P, 0.01, mn)
+    Qv, _ = OC.voxel_trace(Q, 0.01, mn)
+    assert counts == [len(Pv), len(Qv)]
+    s0 = float(np.sum(cKDTree(Qv).query(Pv, k=1)[0] ** 2))
+    s1 = float(np.sum(cKDTree(Pv).query(Qv, k=1)[0] ** 2))
+    assert abs(sums[0] - s0) <= 1e-12 * s0 and abs(sums[1] - s1) <= 1e-12 * s1
+
+
 def test_radius_graph_points_and_boundaries():
     """Closed ball in float64 (SciPy semantics) including exact-boundary pairs."""
     from smartqsm_b200._lib import Engine
