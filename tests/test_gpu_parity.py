@@ -275,6 +275,17 @@ def test_chamfer_value(leafoff_state, small_tree):
     assert abs(st["chamfer"] - cd) <= 1e-9 * cd        # float64 sums in a different order
 
 
+@pytest.mark.parametrize("n,seed,leaf_on,batch_size", [(9000, 21, False, 16), (15000, 22, True, 16), (22000, 23, True, 3),
+                                                     (40000, 24, False, 5), (6000, 25, True, 1)])
+def test_single_iteration_more_trees(n, seed, leaf_on, batch_size):
+    """The whole per-iteration parity check (voxels, winners, rulebooks, activations, outputs) on further seeded trees,
+    both checkpoints, several batch sizes - fixed fixtures alone once hid a data-dependent mismatch."""
+    from oracle import weights
+    from smartqsm_b200.synthetic import make_tree
+    state = weights.load_state("leafon" if leaf_on else "leafoff")
+    check_iteration(state, make_tree(n, seed, leaf_on), batch_size=batch_size)
+
+
 @pytest.mark.parametrize("n,seed", [(12000, 2), (12000, 3), (30000, 2), (60000, 4)])
 def test_chamfer_voxel_counts_and_sums(leafoff_state, n, seed):
     """Both directions of the monitor against Open3D's definition restated in float64: the voxel grids must hold the same
