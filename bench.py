@@ -328,14 +328,15 @@ def main_b200(args):
         if dom:
             f = fams[dom]
             ach = f["bytes"] / (f["ms"] * 1e-3) / 1e9
-            traffic = None
+            traffic, traffic_note = None, None
             try:    # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture of this command
                 tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
                 traffic = tr.get(args.workload, {}).get(dom)
+                traffic_note = tr.get("_note")
             except Exception:
                 pass
             roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                        "frac": ach / hbm_peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                         "avg_launch_ms": f["ms"] / f["launches"], "launches": f["launches"],
                         "algorithmic_bytes_per_launch": f["bytes"] / f["launches"],
                         "gflops_fp32": f["flops"] / (f["ms"] * 1e-3) / 1e9 if f["flops"] else None,

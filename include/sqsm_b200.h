@@ -42,7 +42,8 @@ typedef struct SqsmConfig {
                                            0 = library default (4), 1 = fp32 FFMA everywhere,
                                            2 = tcgen05 3xTF32 split (fp32-class accuracy),
                                            3 = tcgen05 single-pass TF32 (reduced precision, App. D.4),
-                                           4 = tcgen05 3xFP16 split (fp32-class; activations must stay < 3e4) */
+                                           4 = tcgen05 3xFP16 split (fp32-class; activations must stay < 3e4),
+                                           5 = as 4 with the TMA tile::gather4 kernel where it covers the shape */
     int32_t reserved[6];
 } SqsmConfig;
 
