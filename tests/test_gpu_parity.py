@@ -391,3 +391,54 @@ def test_single_tree_sharded_equals_single_gpu(random_state, world):
             P, D = e.result()
             assert np.array_equal(P, P0) and np.array_equal(D, D0)
     assert sum(1 for x in st["segment_sizes"] if x > 0) >= 2      # the work really was split
+
+
+# ---- size-independent properties at the sizes of the other BASELINE configs (the oracle cannot follow there)
+
+def test_c2_size_latch_and_rerun_identity(leafoff_state):
+    """C2-sized run (5 M-point leaf-off tree, reference hyper-parameters): the whole stage is deterministic (two runs are
+    bit-identical) and memoising a rejected thunk (latch) does not change a single output value, skeletal id or edge."""
+    from smartqsm_b200.synthetic import make_tree
+    pts = make_tree(5_000_000, 2)
+    outs = []
+    for latch in (False, True, False):
+        eng = make_engine(leafoff_state, batch_size=16, max_iteration=10, monitored_by_chamfer_distance=True, latch_early_stop=latch)
+        eng.set_points(pts)
+        stats = [eng.contract_step() for _ in range(10)]
+        P, D = eng.result()
+        ids, sk, rad = eng.skeletal_sample(0.01)
+        e = eng.radius_graph(0.055, fetch=False)
+        outs.append((P, D, ids, rad, e, [s["accepted"] for s in stats if not s["skipped"]]))
+        eng.close()
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])
+        assert np.array_equal(o[2], outs[0][2]) and np.array_equal(o[3], outs[0][3]) and o[4] == outs[0][4]
+    acc = outs[0][5]
+    assert acc[0] == 1 and len(acc) == 10
+    # contraction only ever removes duplicates of face points: the cloud cannot grow beyond the face-duplication bound
+    assert 0 < len(outs[0][0]) <= int(len(pts) * 1.1)
+    assert np.all(np.diff(outs[0][2]) > 0)                       # skeletal ids: ascending, unique
+
+
+def test_c5_style_sharding_at_2m_points(leafoff_state):
+    """One oversized tree over 3 emulated ranks at 2 M points (C5's partitioning at a size one GPU can replay): state and
+    Chamfer decisions identical to the single-engine run."""
+    import torch
+    from smartqsm_b200.sharding import emulate_sharded_step
+    from smartqsm_b200.synthetic import make_tree
+    pts = make_tree(2_000_000, 5, True)
+    kw = dict(batch_size=16, monitored_by_chamfer_distance=True)
+    ref = make_engine(leafoff_state, **kw)
+    ref.set_points(pts)
+    shards = [make_engine(leafoff_state, **kw) for _ in range(3)]
+    for e in shards:
+        e.set_points(pts)
+    for it in range(3):
+        st_ref = ref.contract_step()
+        st = emulate_sharded_step(shards, True, torch.device("cuda", 0))
+        assert st["accepted"] == st_ref["accepted"]
+        assert abs(st["chamfer"] - st_ref["chamfer"]) <= 1e-12 * st_ref["chamfer"]
+        P0, D0 = ref.result()
+        P, D = shards[it % 3].result()
+        assert np.array_equal(P, P0) and np.array_equal(D, D0)
+    assert sum(1 for x in st["segment_sizes"] if x > 0) == 3
