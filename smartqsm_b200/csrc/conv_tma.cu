@@ -120,7 +120,6 @@ __global__ void __launch_bounds__(kTmThreads, 1) k_conv_tma(const __grid_constan
         #pragma unroll
         for (int d = 0; d < PF; ++d)
             if (warp + d * T::PW < total) load_rows(warp + d * T::PW, rows[d]);
-        int it = 0;
         for (int q0 = warp; q0 < total; q0 += (PF + 1) * T::PW) {
             #pragma unroll
             for (int d = 0; d <= PF; ++d) {                     // static register rotation
@@ -150,7 +149,6 @@ __global__ void __launch_bounds__(kTmThreads, 1) k_conv_tma(const __grid_constan
                 }
             }
         }
-        (void)it;
     } else if (warp >= kTmProdWarps && warp < kTmProdWarps + 4) {
         // ===================== epilogue: TMEM -> registers -> residual / select -> global =====================
         const int te = t - kTmProdWarps * 32;              // tile row, also the TMEM lane
