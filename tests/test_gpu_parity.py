@@ -442,3 +442,42 @@ def test_c5_style_sharding_at_2m_points(leafoff_state):
         P, D = shards[it % 3].result()
         assert np.array_equal(P, P0) and np.array_equal(D, D0)
     assert sum(1 for x in st["segment_sizes"] if x > 0) == 3
+
+
+def test_error_paths(leafoff_state):
+    """Misuse fails loudly (RuntimeError carrying sqsm_last_error) instead of producing garbage."""
+    from smartqsm_b200._lib import Engine
+    eng = Engine(batch_size=16)
+    with pytest.raises(RuntimeError):
+        eng.contract_step()                                     # no weights, no points
+    eng.load_state_dict(leafoff_state)
+    with pytest.raises(RuntimeError):
+        eng.contract_step()                                     # no points
+    with pytest.raises(RuntimeError):
+        eng.set_points(np.zeros((0, 3)))                        # empty cloud
+    bad = np.random.default_rng(0).uniform(0, 1, (1000, 3))
+    bad[17, 1] = np.nan
+    eng.set_points(bad)
+    with pytest.raises(RuntimeError):
+        eng.contract_step()                                     # non-finite coordinate
+    bad[17, 1] = np.inf
+    eng.set_points(bad)
+    with pytest.raises(RuntimeError):
+        eng.contract_step()
+    incomplete = {k: v for k, v in leafoff_state.items() if not k.startswith("offset_linear")}
+    with pytest.raises(RuntimeError):
+        Engine().load_state_dict(incomplete)                    # missing tensors
+    # the engine stays usable after an error
+    good = np.random.default_rng(1).uniform(0, 1, (2000, 3))
+    eng.set_points(good)
+    assert eng.contract_step()["n_out"] > 0
+
+
+def test_cube_sample_above_2_pow_24_points_raises(leafoff_state):
+    """F7: the reference carries the point index through a float32 column, exact only below 2^24 points per cube sample;
+    the engine refuses instead of silently mixing points up."""
+    eng = make_engine(leafoff_state, batch_size=16)
+    pts = np.random.default_rng(2).uniform(0.5, 3.5, ((1 << 24) + 1000, 3))        # one 4 m cube
+    eng.set_points(pts)
+    with pytest.raises(RuntimeError, match="2\\^24|16777216"):
+        eng.contract_step()
