@@ -481,3 +481,25 @@ def test_cube_sample_above_2_pow_24_points_raises(leafoff_state):
     eng.set_points(pts)
     with pytest.raises(RuntimeError, match="2\\^24|16777216"):
         eng.contract_step()
+
+
+def test_multi_pass_iteration_is_bit_identical(random_state, monkeypatch):
+    """Clouds whose cube samples do not fit one pass (> 48 M entries; a 200 M-point scan on one GPU) are processed in
+    several batch-aligned passes; forcing tiny passes must not change a bit of the state or the Chamfer decisions."""
+    from smartqsm_b200.synthetic import make_tree
+    pts = make_tree(150000, 31, True)
+    kw = dict(batch_size=2, monitored_by_chamfer_distance=True)
+    ref = make_engine(random_state, **kw)
+    monkeypatch.setenv("SQSM_MAX_ENTRIES_PER_PASS", "30000")
+    multi = make_engine(random_state, **kw)
+    monkeypatch.delenv("SQSM_MAX_ENTRIES_PER_PASS")
+    ref.set_points(pts)
+    multi.set_points(pts)
+    for it in range(3):
+        a, b = ref.contract_step(), multi.contract_step()
+        assert (a["n_vox"], a["n_out"], a["accepted"]) == (b["n_vox"], b["n_out"], b["accepted"])
+        assert a["chamfer"] == b["chamfer"] or abs(a["chamfer"] - b["chamfer"]) <= 1e-12 * a["chamfer"]
+        Pa, Da = ref.result()
+        Pb, Db = multi.result()
+        assert np.array_equal(Pa, Pb) and np.array_equal(Da, Db)
+    assert b["gpu_launches"] > 2 * a["gpu_launches"], "the small limit must really have split the iteration into passes"
