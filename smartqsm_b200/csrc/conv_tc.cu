@@ -54,12 +54,12 @@ struct TcArgs {
 
 constexpr int kTcMaxStages = 6;       // shared-memory ring (A hi/lo + B hi/lo per stage), as many as fit 227 KB
 constexpr int kTcPrefetch = 3;        // chunks of gather loads in flight per producer thread (registers)
-constexpr int kTcGroups = 2;          // producer groups; group g gathers chunks g, g+G, ... (thread-level parallelism:
-                                      // one warp per SM sub-partition cannot hide its own issue latencies)
+// producer groups (template parameter GR): group g gathers chunks g, g+GR, ... (thread-level parallelism: one warp per SM
+// sub-partition cannot hide its own issue latencies).  Measured per C3 step: 3 groups beat 2 for the 16-channel sources
+// (16->16: 137 -> 124 ms, 32->16: 88 -> 81 ms) and lose for the wider ones (64->32: 71 -> 78 ms).
 constexpr int kTcProducers = 128;     // threads per producer group; thread t owns tile row t
-constexpr int kTcProdWarps = kTcGroups * 4;
 constexpr int kTcEpilogue = 128;      // next 4 warps: TMEM -> registers -> global; thread owns one tile row
-constexpr int kTcThreads = kTcGroups * kTcProducers + kTcEpilogue + 32;   // last warp: MMA issuer
+__host__ __device__ constexpr int tc_threads(int gr) { return gr * kTcProducers + kTcEpilogue + 32; }   // last warp: MMA issuer
 constexpr uint32_t kTmemCols = 256;   // two accumulator stages of up to 128 columns ([hi*hi + lo*hi | hi*lo] when PRECISE)
 
 __host__ __device__ constexpr int tc_stages(int np) {
@@ -71,8 +71,9 @@ __host__ __device__ constexpr int tc_stages(int np) {
 // F16 = true : FP16 operands (2 B), 64 K elements per chunk row, kind::f16 - half the bytes to gather, half the
 //              LDGSTS instructions and half the shared-memory operand traffic per K element; the 2-term split
 //              hi = fp16(x), lo = fp16(x - hi) carries the same 22 mantissa bits as the TF32 split
-template <int CI, int CO, int KV, bool CAT, bool PRECISE, bool F16>
-__global__ void __launch_bounds__(kTcThreads, 1) k_conv_tc(const __grid_constant__ TcArgs a) {
+template <int CI, int CO, int KV, bool CAT, bool PRECISE, bool F16, int GR>
+__global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_constant__ TcArgs a) {
+    constexpr int kTcGroups = GR, kTcProdWarps = GR * 4;
     constexpr int KT = KV * CI;                       // GEMM K
     constexpr int ES = F16 ? 2 : 4;                   // operand element size
     constexpr int CE = 128 / ES;                      // K elements per chunk row (128 B)
@@ -430,6 +431,7 @@ std::vector<float> make_tc_weight_image_f16(const float* w_kcico, int kv, int ci
 
 template <int CI, int CO, int KV, bool CAT>
 static void launch_tc(Ctx& cx, const TcArgs& a0, bool precise, bool f16) {
+    constexpr int GR = ((CAT ? CI / 2 : CI) == 16 && KV == 27) ? 3 : 2;      // FP16 kernels only (the default path)
     TcArgs a = a0;
     if (a.n_out <= 0) return;
     a.n_tiles = div_up(a.n_out, 128);
@@ -437,17 +439,17 @@ static void launch_tc(Ctx& cx, const TcArgs& a0, bool precise, bool f16) {
     constexpr size_t smem = (size_t)tc_stages(NP) * (2 * 128 * 128 + 2 * NP * 128) + 1024;
     int grid = std::min(a.n_tiles, kNumSMs);
     if (f16) {
-        auto kern = k_conv_tc<CI, CO, KV, CAT, true, true>;
+        auto kern = k_conv_tc<CI, CO, KV, CAT, true, true, GR>;
         SQSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kTcThreads, smem, cx.st>>>(a);
+        kern<<<grid, tc_threads(GR), smem, cx.st>>>(a);
     } else if (precise) {
-        auto kern = k_conv_tc<CI, CO, KV, CAT, true, false>;
+        auto kern = k_conv_tc<CI, CO, KV, CAT, true, false, 2>;
         SQSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kTcThreads, smem, cx.st>>>(a);
+        kern<<<grid, tc_threads(2), smem, cx.st>>>(a);
     } else {
-        auto kern = k_conv_tc<CI, CO, KV, CAT, false, false>;
+        auto kern = k_conv_tc<CI, CO, KV, CAT, false, false, 2>;
         SQSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kTcThreads, smem, cx.st>>>(a);
+        kern<<<grid, tc_threads(2), smem, cx.st>>>(a);
     }
     cx.launches++;
 }
