@@ -505,7 +505,10 @@ static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, boo
     const ConvW& w = nw.conv.at(name);
     if (produce) produce->ready = false;
     if (n_out <= 0) return;
-    const bool use_tc = nw.mode != 0 && w.wimg && w.co >= nw.tc_min_co;
+    // tensor cores from tc_min_co output channels up, plus the level-0 decoder conv on the concatenated 16 channels
+    // (16 -> 8, 27 offsets: 51 vs 66 ms per C3 step on FFMA; the other 8-channel layers are faster on FFMA)
+    const bool use_tc = nw.mode != 0 && w.wimg &&
+                        (w.co >= nw.tc_min_co || (nw.mode >= 3 && cat && w.ci == 16 && w.co == 8 && w.kv == 27));
     // per-kernel scope: algorithmic bytes of SURVEY 8(d): features in + out, rulebook entries, residual re-read
     char fam[64];
     snprintf(fam, sizeof(fam), "conv_%s_ci%d_co%d_k%d", use_tc ? "tc" : "ffma", w.ci, w.co, w.kv);
