@@ -3,26 +3,27 @@
 //
 // Every sparse convolution of the U-Net is a GEMM  D[rows, C_out] = A[rows, KV*C_in] . W[KV*C_in, C_out]
 // whose A operand is gathered through the output-stationary rulebook (nbr[k][row] = input row or -1,
-// zero when absent).  For C >= 16 the fp32 FFMA pipe is the bound of the SIMT kernel in conv.cu, so the
-// 16/32/64-channel layers run here instead:
+// zero when absent).  The 16/32/64-channel layers (and the 16 -> 8 decoder conv) run here:
 //
 //   * a persistent CTA per SM walks tiles of 128 output rows;
-//   * the activated input is split once per element into TF32 "hi" and "lo" arrays (k_act_split);
-//   * 128 producer threads gather the K dimension in chunks of 32 floats (128 B per row) with cp.async
-//     (LDGSTS, 16 B, zero-fill for absent neighbours) straight into two SWIZZLE_128B K-major shared-memory
-//     tiles (hi, lo); the matching weight chunk (pre-split, pre-swizzled on the host) is copied next to
-//     them; completion is tracked by cp.async.mbarrier.arrive, so a ring of STAGES chunks is in flight
-//     without holding registers or scoreboard slots (a register-staged gather stalls in order on the
-//     dependent rulebook -> row loads; measured in profiles/);
-//   * one thread issues tcgen05.mma.kind::tf32 (M=128, N=C_out, K=8) three times per 32-byte K step
-//     (hi*hi + lo*hi + hi*lo: "3xTF32", error ~2^-22 per product, i.e. fp32-class accuracy; the reduced
-//     single-pass mode of App. D.4 is a template switch) accumulating in TMEM, and releases the stage with
-//     tcgen05.commit;
-//   * the producer threads then become the epilogue: tcgen05.ld their accumulator row from TMEM, add the
-//     residual, apply the "batch did not descend" select and store the row.
+//   * the activated input is split once per element into "hi" and "lo" operand arrays - FP16 (default: 2-term split,
+//     hi = fp16(x), lo = fp16(x - hi)) or TF32 - by k_act_split*, or directly by the epilogue of the convolution that
+//     produced it when this layer is its only consumer;
+//   * GR producer groups of 128 threads (GR = 2 or 3) gather the K dimension in chunks of 128 bytes per row with
+//     cp.async (LDGSTS, 16 B, zero-fill for absent neighbours) straight into two SWIZZLE_128B K-major shared-memory
+//     tiles (hi, lo); the matching weight chunk (pre-split, pre-swizzled on the host, W_hi rows then W_lo rows) is
+//     copied next to them; completion is tracked by cp.async.mbarrier.arrive, so a ring of up to 6 chunks is in flight
+//     without holding registers or scoreboard slots (a register-staged gather stalls in order on the dependent
+//     rulebook -> row loads; measured in profiles/); rulebook entries are prefetched 7 chunks ahead;
+//   * one thread issues tcgen05.mma (M = 128, 32 bytes of K per instruction) TWICE per K step:
+//     A_hi . [W_hi | W_lo] with N = 2*C_out into two halves of the TMEM accumulator, then A_lo . W_hi with N = C_out
+//     into the first half (hi*hi + lo*hi + hi*lo overall: error ~2^-22 per product, fp32-class accuracy; the reduced
+//     single-pass TF32 mode of App. D.4 is a template switch), and releases the stage with tcgen05.commit;
+//   * four epilogue warps tcgen05.ld the accumulator (two stages, so the next tile's MMAs overlap), sum the halves, add
+//     the residual, apply the "batch did not descend" select, store - and optionally write the consumer's operands.
 //
-// TMA is not used for A: the rows of a tile come from arbitrary addresses (a gather), which is exactly
-// what TMA cannot express; the weight chunk is small and shared by all tiles (L2 resident).
+// The gather uses LDGSTS rather than TMA: conv_tma.cu is the same kernel on cp.async.bulk.tensor tile::gather4 and is
+// 10-25 % slower in the pipeline (profiles/r01_gather_microbench_notes.md); the weight chunk is small and L2 resident.
 #include "engine.h"
 #include "tc_ptx.cuh"
 #include <cuda_fp16.h>
