@@ -45,6 +45,16 @@ void sort_pairs_u32(Ctx& cx, const uint32_t* d_kin, uint32_t* d_kout, const uint
     cx.launches += 2 * ((end_bit - begin_bit + 7) / 8) + 1;
 }
 
+void segmented_sort_u32(Ctx& cx, const uint32_t* d_in, uint32_t* d_out, int64_t n, int64_t n_segments, const int64_t* d_off) {
+    if (n <= 0 || n_segments <= 0) return;
+    SQSM_CHECK(n < (1ll << 31) && n_segments < (1ll << 31), "segmented sort: more than 2^31 items");
+    size_t tb = 0;
+    SQSM_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, tb, d_in, d_out, (int)n, (int)n_segments, d_off, d_off + 1, cx.st));
+    DBuf<uint8_t> tmp((int64_t)tb + 16, cx.st);
+    SQSM_CUDA(cub::DeviceSegmentedSort::SortKeys(tmp.p, tb, d_in, d_out, (int)n, (int)n_segments, d_off, d_off + 1, cx.st));
+    cx.launches += 3;
+}
+
 // ------------------------------------------------------------------ kernels
 
 // Insert every entry's brick key; the thread that claims a slot appends the key to the list.

@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(256) k_radius_pairs(const float* __restrict__ 
                                                       const uint32_t* __restrict__ cell_of, int64_t n,
                                                       const int32_t* __restrict__ bnbr, const int32_t* __restrict__ cstart,
                                                       double r2, int32_t* __restrict__ cnt, const int64_t* __restrict__ off,
-                                                      int64_t* __restrict__ edges) {
+                                                      uint32_t* __restrict__ ebuf_i, uint32_t* __restrict__ ebuf_j) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const uint32_t i = order[s];
@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(256) k_radius_pairs(const float* __restrict__ 
             double dx = x - (double)P[3 * (size_t)j], dy = y - (double)P[3 * (size_t)j + 1], dz = z - (double)P[3 * (size_t)j + 2];
             double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
             if (d2 <= r2) {
-                if (MODE == 1) { edges[2 * (o + c)] = (int64_t)i; edges[2 * (o + c) + 1] = (int64_t)j; }
+                if (MODE == 1) { ebuf_i[o + c] = i; ebuf_j[o + c] = j; }
                 ++c;
             }
         }
@@ -582,17 +582,11 @@ __global__ void __launch_bounds__(256) k_radius_pairs(const float* __restrict__ 
     if (MODE == 0) cnt[i] = c;
 }
 
-// ascending j inside every node's segment (the merged edge list is lexicographic, :158)
-__global__ void __launch_bounds__(256) k_sort_segments(int64_t* __restrict__ edges, const int64_t* __restrict__ off, int64_t n) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int64_t b = off[i], e = off[i + 1];
-    for (int64_t a = b + 1; a < e; ++a) {
-        int64_t v = edges[2 * a + 1];
-        int64_t p = a - 1;
-        while (p >= b && edges[2 * p + 1] > v) { edges[2 * (p + 1) + 1] = edges[2 * p + 1]; --p; }
-        edges[2 * (p + 1) + 1] = v;
-    }
+// (i, sorted j) 32-bit keys -> the int64 [E][2] edge list of the ABI; fully coalesced
+__global__ void __launch_bounds__(256) k_edges_expand(const uint32_t* __restrict__ ei, const uint32_t* __restrict__ ej, int64_t n,
+                                                      longlong2* __restrict__ edges) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) edges[e] = make_longlong2((long long)ei[e], (long long)ej[e]);
 }
 
 __global__ void __launch_bounds__(256) k_iota_u32(uint32_t* __restrict__ a, int64_t n) {
@@ -650,7 +644,7 @@ void radius_graph(Ctx& cx, const float* d_pts, int64_t m, double r, DBuf<int64_t
     SQSM_CUDA(cudaMemsetAsync(cnt.p + m, 0, sizeof(int32_t), st));
     const double r2 = r * r;
     k_radius_pairs<0><<<div_up(m, 256), 256, 0, st>>>(d_pts, order.p, cell_sorted.p, m, map.bnbr.p, cstart.p, r2, cnt.p,
-                                                      nullptr, nullptr);
+                                                      nullptr, nullptr, nullptr);
     DBuf<int64_t> cnt64(m + 1, st), off(m + 1, st);
     k_i32_to_i64<<<div_up(m + 1, 256), 256, 0, st>>>(cnt.p, cnt64.p, m + 1);
     cx.launches += 2;
@@ -660,10 +654,16 @@ void radius_graph(Ctx& cx, const float* d_pts, int64_t m, double r, DBuf<int64_t
     SQSM_CUDA(cudaStreamSynchronize(st));
     *n_edges = E;
     if (E == 0) return;
-    edges.alloc(2 * E, st);
+    // fill (i, j) as 32-bit keys, sort j ascending inside every node's segment (the merged edge list is lexicographic,
+    // :158) with a segmented sort - no quadratic worst case for dense clusters - then expand to the int64 pairs of the ABI
+    SQSM_CHECK(E < (1ll << 31), "radius graph: more than 2^31 edges");
+    DBuf<uint32_t> ebuf_i(E, st), ebuf_j(E, st), ebuf_s(E, st);
     k_radius_pairs<1><<<div_up(m, 256), 256, 0, st>>>(d_pts, order.p, cell_sorted.p, m, map.bnbr.p, cstart.p, r2, nullptr,
-                                                      off.p, edges.p);
-    k_sort_segments<<<div_up(m, 256), 256, 0, st>>>(edges.p, off.p, m);
+                                                      off.p, ebuf_i.p, ebuf_j.p);
+    segmented_sort_u32(cx, ebuf_j.p, ebuf_s.p, E, m, off.p);
+    ebuf_j.release();
+    edges.alloc(2 * E, st);
+    k_edges_expand<<<div_up(E, 256), 256, 0, st>>>(ebuf_i.p, ebuf_s.p, E, reinterpret_cast<longlong2*>(edges.p));
     cx.launches += 2;
 }
 
