@@ -332,6 +332,17 @@ def test_radius_graph_points_and_boundaries():
     assert eng.radius_graph_points(far, 0.055).shape == (0, 2)
 
 
+def test_radius_graph_dense_cluster():
+    """Thousands of neighbours per node (a knot of skeletal points): the per-node lists come out of a segmented sort, so
+    there is no quadratic blow-up and the edge list still equals SciPy's."""
+    from smartqsm_b200._lib import Engine
+    rng = np.random.default_rng(3)
+    pts = np.concatenate([rng.normal(0, 0.012, (3500, 3)), rng.uniform(-0.5, 0.5, (2000, 3))]).astype(np.float32)
+    e_g = Engine().radius_graph_points(pts, 0.055)
+    e_o = OC.radius_edges(pts, 0.055)
+    assert len(e_o) > 3_000_000 and np.array_equal(e_g, e_o)
+
+
 def test_large_cloud_properties(random_state):
     """Full-size properties (no oracle at this size): structural invariants of one iteration over a
     1 M-point tree and bit-identical results when the same input is run twice (determinism: the
