@@ -62,9 +62,9 @@ def parse_args():
 
 def load_state(which: str):
     """Checkpoint blob exported by build() from the reference checkout if present, else seeded
-    random-init weights of the same architecture (oracle/weights.py)."""
-    from oracle import weights
-    return weights.load_state(which), weights.weights_kind(which)
+    random-init weights of the same architecture (smartqsm_b200/checkpoints.py; no oracle code on the GPU arm)."""
+    from smartqsm_b200 import checkpoints
+    return checkpoints.load_state(which), checkpoints.weights_kind(which)
 
 
 class ClockSampler:

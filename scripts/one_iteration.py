@@ -2,7 +2,7 @@
 import sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import weights
+from smartqsm_b200 import checkpoints as weights
 from smartqsm_b200._lib import Engine
 from smartqsm_b200.synthetic import make_tree
 

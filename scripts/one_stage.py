@@ -1,7 +1,7 @@
 """One contraction thunk + skeletal sampling + radius graph on a synthetic tree (ncu target covering every kernel family)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import weights
+from smartqsm_b200 import checkpoints as weights
 from smartqsm_b200._lib import Engine
 from smartqsm_b200.synthetic import make_tree
 

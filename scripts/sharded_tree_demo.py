@@ -12,7 +12,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import weights  # noqa: E402  (only to fetch the weight blob; the oracle does not run here)
+from smartqsm_b200 import checkpoints as weights
 from smartqsm_b200._lib import Engine  # noqa: E402
 from smartqsm_b200.sharding import ShardedTreeContraction  # noqa: E402
 from smartqsm_b200.synthetic import make_tree  # noqa: E402

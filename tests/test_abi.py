@@ -70,3 +70,21 @@ def test_plugin_interface_mirrors_reference():
     assert registry["thinning"]["spconv_based_contraction"] is SpconvBasedContraction
     for m in ("input", "get_pipeline", "output"):
         assert callable(getattr(SpconvBasedContraction, m))
+
+
+def test_product_package_never_imports_the_oracle():
+    """The oracle is test infrastructure: importing every product module must not pull it in, and no product source
+    mentions it (bench.py may only use it on the cpu_baseline / --impl reference legs)."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); "
+            "import smartqsm_b200, smartqsm_b200._lib, smartqsm_b200.core_algorithms, smartqsm_b200.preprocess, "
+            "smartqsm_b200.sharding, smartqsm_b200.synthetic, smartqsm_b200.checkpoints, smartqsm_b200.build; "
+            "bad = [m for m in sys.modules if m == 'oracle' or m.startswith('oracle.')]; "
+            "assert not bad, bad") % ROOT
+    subprocess.run([sys.executable, "-c", code], check=True)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "smartqsm_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
