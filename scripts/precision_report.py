@@ -16,7 +16,7 @@ for name, dt in (("f32", torch.float32), ("f64", torch.float64)):
     ref[name] = (P, D, tr)
 olv = H.oracle_level_tables(ref["f32"][2], 16)
 rep = {}
-for mode, label in ((1, "ffma"), (2, "tc3"), (4, "f16x3"), (3, "tf32")):
+for mode, label in ((1, "ffma"), (2, "tc3"), (4, "f16x3"), (5, "f16x3_tma"), (3, "tf32")):
     eng = Engine(conv_mode=mode)
     eng.load_state_dict(state)
     eng.debug_capture(True)

@@ -19,9 +19,9 @@ pytestmark = pytest.mark.gpu
 #   ffma  fp32 FFMA everywhere: activations ~5e-7 of the tensor scale, the fp32-vs-fp64 oracle gap is 2e-7
 #   tc3   tcgen05 3xTF32 for the 16-64 channel layers: ~1.5e-5 at the deepest level (the tensor core's fp32
 #         accumulation chain, not the operand split, sets this floor)
-ACT_TOL = {1: 5e-6, 2: 4e-5, 0: 4e-5, 4: 4e-5, 5: 4e-5}      # activations: max |gpu - oracle| / max |oracle| per tensor
+ACT_TOL = {1: 5e-6, 2: 3e-5, 0: 2e-5, 4: 2e-5, 5: 2e-5}      # activations: max |gpu - oracle| / max |oracle| per tensor
 DISP_TOL = {1: 1e-5, 2: 6e-5, 0: 6e-5, 4: 6e-5, 5: 6e-5}     # displacements: relative to max |displacement|
-POS_TOL = {1: 2e-6, 2: 1e-5, 0: 1e-5, 4: 1e-5, 5: 1e-5}      # contracted positions: absolute metres on coordinates of ~10 m
+POS_TOL = {1: 2e-6, 2: 8e-6, 0: 4e-6, 4: 4e-6, 5: 4e-6}      # contracted positions: absolute metres on coordinates of ~10 m
 
 
 def make_engine(state, **kw):
