@@ -138,16 +138,19 @@ int  sqsm_radius_graph_points(sqsm_handle h, const float* h_points_xyz, int64_t 
  * Open3D voxel_down_sample, float64 voxel means (:889), Open3D remove_statistical_outlier
  * (:895-898), density-adaptation scale = voxel_down_size / mean nearest-neighbour distance
  * (SciPy KDTree, :908-913).  Output order: 8^3-voxel bricks by (z, y, x) brick index, then z, y, x
- * inside the brick (Open3D's unordered_map order is not reproducible).  filter ==
- * "radius_outlier_removal" (:899-902) is not provided (no shipped config uses it). */
+ * inside the brick (Open3D's unordered_map order is not reproducible).  Both filters of the entry point are provided:
+ * statistical_outlier_removal (:895-898) and radius_outlier_removal (:899-902, Open3D: more than nb_points points,
+ * itself included, with squared distance < radius^2). */
 typedef struct SqsmPrepConfig {
     double  voxel_down_size;      /* configs/*.yaml: voxel_down_size (0.01) */
     double  std_ratio;            /* kwargs_for_filter.std_ratio (4.0) */
-    int32_t filter;               /* 0 = none, 1 = statistical_outlier_removal */
+    int32_t filter;               /* 0 = none, 1 = statistical_outlier_removal, 2 = radius_outlier_removal */
     int32_t nb_neighbors;         /* kwargs_for_filter.nb_neighbors (10); 1..32 */
     int32_t density_adaptation;   /* using_density_adaptation_in_skeletonization */
     int32_t keep_debug;           /* keep the intermediate arrays for sqsm_debug_prepared */
-    int32_t reserved[4];
+    double  radius;               /* filter 2: kwargs_for_filter.radius */
+    int32_t nb_points;            /* filter 2: kwargs_for_filter.nb_points */
+    int32_t reserved[1];
 } SqsmPrepConfig;
 
 typedef struct SqsmPrepStats {
@@ -168,8 +171,8 @@ int  sqsm_prepared_size(sqsm_handle h, int64_t* n_kept, int64_t* n_voxel);
 int  sqsm_get_prepared(sqsm_handle h, double* h_points_xyz);
 /* CoreAlgorithmBase.input(points = prepared * scale) without the host round trip (:922 + epoch-1 cast). */
 int  sqsm_set_points_prepared(sqsm_handle h);
-/* keep_debug only: voxel means float64[n_voxel,3], avg k-NN distance float64[n_voxel], keep uint8[n_voxel]
- * (the last two only with filter == 1); any pointer may be NULL. */
+/* keep_debug only: voxel means float64[n_voxel,3], avg k-NN distance float64[n_voxel] (filter 1; with filter 2 the
+ * neighbour count as a double), keep uint8[n_voxel] (the last two only with a filter); any pointer may be NULL. */
 int  sqsm_debug_prepared(sqsm_handle h, double* h_voxel_means, double* h_avg_distance, uint8_t* h_keep);
 
 /* ---- parity / inspection hooks (integer outputs of the LAST sqsm_contract_step) --------

@@ -76,12 +76,19 @@ def remove_statistical_outlier(points: np.ndarray, nb_neighbors: int, std_ratio:
     return keep, avg, (cloud_mean, std, thr)
 
 
-def remove_radius_outlier(points: np.ndarray, nb_points: int, radius: float) -> np.ndarray:
-    """Open3D ``remove_radius_outlier`` (``smartqsm.py:899-902``): keep points with more than ``nb_points``
-    points (itself included) inside the closed ball of ``radius``."""
+def remove_radius_outlier(points: np.ndarray, nb_points: int, radius: float):
+    """Open3D ``remove_radius_outlier`` (``smartqsm.py:899-902``): ``SearchRadius`` hands ``radius**2`` to nanoflann,
+    whose ``RadiusResultSet`` keeps ``dist2 < radius2`` (open ball, the point itself included); a point stays when it has
+    MORE than ``nb_points`` such neighbours.  Returns ``(kept index i64[K], count i64[N])``."""
     p = np.asarray(points, np.float64)
-    cnt = cKDTree(p).query_ball_point(p, float(radius), return_length=True)
-    return np.nonzero(cnt > int(nb_points))[0].astype(np.int64)
+    r2 = float(radius) * float(radius)
+    lists = cKDTree(p).query_ball_point(p, float(radius) * (1.0 + 1e-9))          # superset; exact test below
+    cnt = np.zeros(len(p), np.int64)
+    for i, nb in enumerate(lists):
+        d = p[nb] - p[i]
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        cnt[i] = int(np.count_nonzero(d2 < r2))
+    return np.nonzero(cnt > int(nb_points))[0].astype(np.int64), cnt
 
 
 def density_scale(points: np.ndarray, voxel: float) -> float:
@@ -116,7 +123,7 @@ def prepare_cloud(points: np.ndarray, voxel_down_size: float = 0.01, filter: Opt
         keep, _, stats = remove_statistical_outlier(v, nb_neighbors, std_ratio)
         kept = v[keep]
     elif filter == "radius_outlier_removal":
-        kept = v[remove_radius_outlier(v, nb_points, radius)]
+        kept = v[remove_radius_outlier(v, nb_points, radius)[0]]
     else:
         raise NotImplementedError(f"Filter {filter} is not implemented.")            # :903-904
     scale = density_scale(kept, voxel_down_size) if density_adaptation else 1.0      # :908-913

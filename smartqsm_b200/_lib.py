@@ -43,7 +43,8 @@ class SqsmIterStats(C.Structure):
 class SqsmPrepConfig(C.Structure):
     _fields_ = [
         ("voxel_down_size", C.c_double), ("std_ratio", C.c_double), ("filter", C.c_int32), ("nb_neighbors", C.c_int32),
-        ("density_adaptation", C.c_int32), ("keep_debug", C.c_int32), ("reserved", C.c_int32 * 4),
+        ("density_adaptation", C.c_int32), ("keep_debug", C.c_int32), ("radius", C.c_double), ("nb_points", C.c_int32),
+        ("reserved", C.c_int32 * 1),
     ]
 
 
@@ -198,12 +199,13 @@ class Engine:
 
     # ---- cloud preparation (row f2)
     def prepare_cloud(self, points: np.ndarray, *, voxel_down_size: float = 0.01, filter: int = 1, nb_neighbors: int = 10,
-                      std_ratio: float = 4.0, density_adaptation: bool = True, keep_debug: bool = False) -> dict:
+                      std_ratio: float = 4.0, density_adaptation: bool = True, keep_debug: bool = False,
+                      nb_points: int = 0, radius: float = 0.0) -> dict:
         a = np.ascontiguousarray(points, dtype=np.float64)
         assert a.ndim == 2 and a.shape[1] == 3
         cfg = SqsmPrepConfig(voxel_down_size=voxel_down_size, std_ratio=std_ratio, filter=int(filter),
                              nb_neighbors=int(nb_neighbors), density_adaptation=int(density_adaptation),
-                             keep_debug=int(keep_debug))
+                             keep_debug=int(keep_debug), radius=float(radius), nb_points=int(nb_points))
         st = SqsmPrepStats()
         self._check(self._lib.sqsm_prepare_cloud_f64(self._h, _ptr(a), a.shape[0], C.byref(cfg), C.byref(st)), "prepare_cloud")
         return st.as_dict()

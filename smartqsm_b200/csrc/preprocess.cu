@@ -313,6 +313,46 @@ __global__ void __launch_bounds__(128) k_knn_far(const Brick* __restrict__ brick
     }
 }
 
+// Open3D remove_radius_outlier: number of voxel means with squared distance < r2 (the query itself included).  Thread per
+// query; the bricks within ceil(r / edge) rings are taken from the neighbour table (ring 1) or probed in the hash, and
+// skipped when their box is farther than r.  The count is stored as a double (same array as the k-NN averages).
+__global__ void __launch_bounds__(128) k_radius_count(const Brick* __restrict__ bricks, const int32_t* __restrict__ bnbr, BrickHash h,
+                                                      const int32_t* __restrict__ row_brick, const double* __restrict__ V, int64_t rows,
+                                                      const __grid_constant__ PrepGrid g, double r2, int rings,
+                                                      double* __restrict__ out) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const double qx = V[3 * r], qy = V[3 * r + 1], qz = V[3 * r + 2];
+    const int b = row_brick[r];
+    const uint64_t key = bricks[b].key;
+    const int bz = (int)key_z(key), by = (int)key_y(key), bx = (int)key_x(key);
+    const double edge = 8.0 * g.voxel, slack = 1e-9 * edge;
+    int count = 0;
+    for (int dz = -rings; dz <= rings; ++dz)
+        for (int dy = -rings; dy <= rings; ++dy)
+            for (int dx = -rings; dx <= rings; ++dx) {
+                const int z = bz + dz, y = by + dy, x = bx + dx;
+                if (z < 0 || y < 0 || x < 0 || z > 65535 || y > 65535 || x > 65535) continue;
+                // distance from the query to the brick box
+                const double ox = g.vmin[0] + (double)x * edge, oy = g.vmin[1] + (double)y * edge, oz = g.vmin[2] + (double)z * edge;
+                const double gx = fmax(fmax(ox - qx, qx - ox - edge) - slack, 0.0), gy = fmax(fmax(oy - qy, qy - oy - edge) - slack, 0.0),
+                             gz = fmax(fmax(oz - qz, qz - oz - edge) - slack, 0.0);
+                if (gx * gx + gy * gy + gz * gz >= r2) continue;
+                int id;
+                if (dz >= -1 && dz <= 1 && dy >= -1 && dy <= 1 && dx >= -1 && dx <= 1) id = bnbr[(size_t)b * 32 + (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)];
+                else id = hash_find(h, pack_key(0u, (uint32_t)z, (uint32_t)y, (uint32_t)x));
+                if (id < 0) continue;
+                const int cb = bricks[id].base, cn = bricks[id].count;
+                for (int i = 0; i < cn; ++i) {
+                    const size_t c = (size_t)(cb + i);
+                    const double ex = V[3 * c] - qx, ey = V[3 * c + 1] - qy, ez = V[3 * c + 2] - qz;
+                    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+                    count += d2 < r2 ? 1 : 0;
+                }
+            }
+    out[r] = (double)count;
+}
+
 // fixed-tree sums: block b adds elements b, b + G, ... in order per thread, then a shared-memory tree; the host adds the
 // G partials in order.  f selects the summand: 0 = x (x > 0), 1 = (x - c)^2 (x > 0), 2 = x (flag set)
 __global__ void __launch_bounds__(256) k_partial_sums(const double* __restrict__ x, const uint8_t* __restrict__ flag, int64_t n, int f,
@@ -345,11 +385,12 @@ double fixed_sum(Ctx& cx, const double* d_x, const uint8_t* d_flag, int64_t n, i
     return s;
 }
 
-__global__ void __launch_bounds__(256) k_keep_flags(const double* __restrict__ avg, int64_t n, double thr, uint8_t* __restrict__ keep,
-                                                    int32_t* __restrict__ keep_i) {
+// filter 1: 0 < avg < thr (statistical); filter 2: count > thr (radius, thr = nb_points)
+__global__ void __launch_bounds__(256) k_keep_flags(const double* __restrict__ avg, int64_t n, double thr, int filter,
+                                                    uint8_t* __restrict__ keep, int32_t* __restrict__ keep_i) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const bool k = avg[i] > 0.0 && avg[i] < thr;
+    const bool k = filter == 1 ? (avg[i] > 0.0 && avg[i] < thr) : (avg[i] > thr);
     keep[i] = k ? 1 : 0;
     keep_i[i] = k ? 1 : 0;
 }
@@ -399,8 +440,9 @@ void prepare_cloud(Ctx& cx, const double* h_xyz, int64_t n, const SqsmPrepConfig
     cudaStream_t st = cx.st;
     SQSM_CHECK(h_xyz && n > 0 && n < (1ll << 31), "bad point array");
     SQSM_CHECK(cfg.voxel_down_size > 0.0, "voxel_down_size must be positive");
-    SQSM_CHECK(cfg.filter == 0 || cfg.filter == 1, "filter must be 0 (none) or 1 (statistical_outlier_removal)");
-    SQSM_CHECK(cfg.filter == 0 || (cfg.nb_neighbors >= 1 && cfg.nb_neighbors <= kKnnMax), "nb_neighbors must be 1..32");
+    SQSM_CHECK(cfg.filter >= 0 && cfg.filter <= 2, "filter must be 0 (none), 1 (statistical_outlier_removal) or 2 (radius_outlier_removal)");
+    SQSM_CHECK(cfg.filter != 1 || (cfg.nb_neighbors >= 1 && cfg.nb_neighbors <= kKnnMax), "nb_neighbors must be 1..32");
+    SQSM_CHECK(cfg.filter != 2 || (cfg.radius > 0.0 && cfg.nb_points >= 0), "radius_outlier_removal needs radius > 0 and nb_points >= 0");
     memset(&out, 0, sizeof(out));
     out.n_in = n;
     const int64_t launches0 = cx.launches;
@@ -462,7 +504,7 @@ void prepare_cloud(Ctx& cx, const double* h_xyz, int64_t n, const SqsmPrepConfig
     SQSM_CUDA(cudaEventRecord(ev[1], st));
 
     // ---- search structure shared by the two neighbour queries
-    const bool need_nn = cfg.filter == 1 || cfg.density_adaptation;
+    const bool need_nn = cfg.filter != 0 || cfg.density_adaptation;
     DBuf<int32_t> row_brick;
     DBuf<uint32_t> bitmap;
     BrickBitmap bm{nullptr, 0, 0, 0, 0};
@@ -496,21 +538,32 @@ void prepare_cloud(Ctx& cx, const double* h_xyz, int64_t n, const SqsmPrepConfig
     ps.avg.release();
     ps.keep.release();
     int64_t n_kept = rows;
-    if (cfg.filter == 1) {
-        const int k = (int)std::min<int64_t>(cfg.nb_neighbors, rows);
+    if (cfg.filter != 0) {
+        double thr;
         ps.avg.alloc(rows, st);
-        run_knn(cx, map, bm, row_brick.p, V.p, nullptr, rows, k, g, max_ring, 0, ps.avg.p, &out.n_far_filter);
-        const double cloud_mean = fixed_sum(cx, ps.avg.p, nullptr, rows, 0, 0.0) / (double)rows;
-        const double sq = fixed_sum(cx, ps.avg.p, nullptr, rows, 1, cloud_mean);
-        const double sd = rows > 1 ? std::sqrt(sq / (double)(rows - 1)) : 0.0;
-        const double thr = cloud_mean + cfg.std_ratio * sd;
-        out.cloud_mean = cloud_mean;
-        out.std_dev = sd;
-        out.threshold = thr;
+        if (cfg.filter == 1) {
+            const int k = (int)std::min<int64_t>(cfg.nb_neighbors, rows);
+            run_knn(cx, map, bm, row_brick.p, V.p, nullptr, rows, k, g, max_ring, 0, ps.avg.p, &out.n_far_filter);
+            const double cloud_mean = fixed_sum(cx, ps.avg.p, nullptr, rows, 0, 0.0) / (double)rows;
+            const double sq = fixed_sum(cx, ps.avg.p, nullptr, rows, 1, cloud_mean);
+            const double sd = rows > 1 ? std::sqrt(sq / (double)(rows - 1)) : 0.0;
+            thr = cloud_mean + cfg.std_ratio * sd;
+            out.cloud_mean = cloud_mean;
+            out.std_dev = sd;
+            out.threshold = thr;
+        } else {                                             // remove_radius_outlier (:899-902)
+            const int rings = (int)std::ceil(cfg.radius / (8.0 * cfg.voxel_down_size));
+            SQSM_CHECK(rings <= 64, "radius_outlier_removal: radius above 64 brick edges");
+            k_radius_count<<<div_up(rows, 128), 128, 0, st>>>(map.bricks.p, map.bnbr.p, map.view(), row_brick.p, V.p, rows, g,
+                                                               cfg.radius * cfg.radius, rings, ps.avg.p);
+            cx.launches++;
+            thr = (double)cfg.nb_points;
+            out.threshold = thr;
+        }
         keep.alloc(rows, st);
         DBuf<int32_t> keep_i(rows + 1, st), off(rows + 1, st);
         keep_i.zero();
-        k_keep_flags<<<div_up(rows, 256), 256, 0, st>>>(ps.avg.p, rows, thr, keep.p, keep_i.p);
+        k_keep_flags<<<div_up(rows, 256), 256, 0, st>>>(ps.avg.p, rows, thr, cfg.filter, keep.p, keep_i.p);
         exclusive_scan_i32(cx, keep_i.p, off.p, rows + 1);
         int32_t total = 0;
         SQSM_CUDA(cudaMemcpyAsync(&total, off.p + rows, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -532,7 +585,7 @@ void prepare_cloud(Ctx& cx, const double* h_xyz, int64_t n, const SqsmPrepConfig
     if (cfg.density_adaptation) {
         SQSM_CHECK(n_kept >= 2, "density adaptation needs at least two points");
         DBuf<double> nn(rows, st);
-        run_knn(cx, map, bm, row_brick.p, V.p, cfg.filter == 1 ? keep.p : nullptr, rows, 2, g, max_ring, 1, nn.p, &out.n_far_scale);
+        run_knn(cx, map, bm, row_brick.p, V.p, cfg.filter != 0 ? keep.p : nullptr, rows, 2, g, max_ring, 1, nn.p, &out.n_far_scale);
         const double mean_nn = fixed_sum(cx, nn.p, nullptr, rows, 0, 0.0) / (double)n_kept;     // dropped rows hold -1, distances are > 0
         out.mean_nn = mean_nn;
         scale = cfg.voxel_down_size / mean_nn;
@@ -544,7 +597,7 @@ void prepare_cloud(Ctx& cx, const double* h_xyz, int64_t n, const SqsmPrepConfig
     if (cfg.keep_debug) {
         ps.vox.alloc(rows * 3, st);
         SQSM_CUDA(cudaMemcpyAsync(ps.vox.p, V.p, sizeof(double) * rows * 3, cudaMemcpyDeviceToDevice, st));
-        if (cfg.filter == 1) {
+        if (cfg.filter != 0) {
             ps.keep.alloc(rows, st);
             SQSM_CUDA(cudaMemcpyAsync(ps.keep.p, keep.p, rows, cudaMemcpyDeviceToDevice, st));
         }

@@ -4,7 +4,7 @@
 ``prepare_cloud`` takes the raw float64 cloud and the keys of the reference's YAML config
 (``voxel_down_size``, ``filter``, ``kwargs_for_filter``, ``using_density_adaptation_in_skeletonization``)
 and runs bounding box -> global shift -> translate -> voxel down-sampling (float64 voxel means) ->
-statistical outlier removal -> density-adaptation scale on the GPU through ``libsqsm_b200.so``.
+statistical / radius outlier removal -> density-adaptation scale on the GPU through ``libsqsm_b200.so``.
 No CPU fallback.  ``SpconvBasedContraction.prepare_input(raw_points, ...)`` runs the same preparation on the
 algorithm's own engine and feeds ``points * scale`` to the contraction without a host round trip.
 """
@@ -19,7 +19,7 @@ from ._lib import Engine
 
 __all__ = ["prepare_cloud", "PreparedCloud"]
 
-_FILTERS = {None: 0, "statistical_outlier_removal": 1}
+_FILTERS = {None: 0, "statistical_outlier_removal": 1, "radius_outlier_removal": 2}
 
 
 @dataclass
@@ -49,13 +49,11 @@ def prepare_cloud(points: np.ndarray, *, voxel_down_size: float = 0.01, filter: 
                   engine: Optional[Engine] = None, keep_debug: bool = False, **engine_kwargs) -> PreparedCloud:
     """``entrypoints/smartqsm.py:882-913`` on the GPU.  Keyword names are the reference's config keys."""
     if filter not in _FILTERS:
-        if filter == "radius_outlier_removal":
-            raise NotImplementedError("radius_outlier_removal is not provided by the B200 preparation "
-                                      "(no shipped SmartQSM config uses it)")
         raise NotImplementedError(f"Filter {filter} is not implemented.")                    # :903-904
     kw = dict(kwargs_for_filter or {})
     eng = engine if engine is not None else Engine(device=device, **engine_kwargs)
     st = eng.prepare_cloud(points, voxel_down_size=float(voxel_down_size), filter=_FILTERS[filter],
                            nb_neighbors=int(kw.get("nb_neighbors", 10)), std_ratio=float(kw.get("std_ratio", 4.0)),
+                           nb_points=int(kw.get("nb_points", 0)), radius=float(kw.get("radius", 0.0)),
                            density_adaptation=bool(using_density_adaptation_in_skeletonization), keep_debug=keep_debug)
     return PreparedCloud(global_shift=st["global_shift"], scale=float(st["scale"]), stats=st, _engine=eng)

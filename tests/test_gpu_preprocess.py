@@ -20,15 +20,21 @@ def _check(engine, raw, **cfg):
     filt = cfg.get("filter", "statistical_outlier_removal")
     dens = cfg.get("density_adaptation", True)
     nb, ratio = cfg.get("nb_neighbors", 10), cfg.get("std_ratio", 4.0)
-    ref = OP.prepare_cloud(raw, 0.01, filt, nb, ratio, density_adaptation=dens)
-    st = engine.prepare_cloud(raw, voxel_down_size=0.01, filter=1 if filt else 0, nb_neighbors=nb, std_ratio=ratio,
+    nbp, rad = cfg.get("nb_points", 0), cfg.get("radius", 0.0)
+    code = {None: 0, "statistical_outlier_removal": 1, "radius_outlier_removal": 2}[filt]
+    ref = OP.prepare_cloud(raw, 0.01, filt, nb, ratio, nbp, rad, density_adaptation=dens)
+    st = engine.prepare_cloud(raw, voxel_down_size=0.01, filter=code, nb_neighbors=nb, std_ratio=ratio, nb_points=nbp, radius=rad,
                               density_adaptation=dens, keep_debug=True)
     assert np.array_equal(st["global_shift"], ref.global_shift)
     assert (st["n_in"], st["n_voxel"], st["n_kept"]) == (ref.n_in, ref.n_voxel, ref.n_kept)
     vox, avg, keep = engine.debug_prepared(with_filter=bool(filt))
     v_ref, _ = OP.voxel_down_sample(raw + ref.global_shift[None, :], 0.01)
     assert np.array_equal(vox, v_ref), "voxel means must be bit-identical (input-order sums)"
-    if filt:
+    if filt == "radius_outlier_removal":
+        keep_ref, cnt_ref = OP.remove_radius_outlier(v_ref, nbp, rad)
+        assert np.array_equal(avg.astype(np.int64), cnt_ref), "neighbour counts (open ball, float64) must be identical"
+        assert np.array_equal(np.nonzero(keep)[0], keep_ref)
+    elif filt:
         keep_ref, avg_ref, (mean, std, thr) = OP.remove_statistical_outlier(v_ref, nb, ratio)
         np.testing.assert_allclose(avg, avg_ref, rtol=1e-12, atol=0)
         np.testing.assert_allclose([st["cloud_mean"], st["std_dev"], st["threshold"]], [mean, std, thr], rtol=1e-12)
@@ -54,6 +60,16 @@ def test_prepare_cloud_without_filter_or_scale(engine):
     st, _ = _check(engine, make_raw_scan(20000, 9), filter=None, density_adaptation=False)
     assert st["scale"] == 1.0 and st["n_kept"] == st["n_voxel"]
     _check(engine, make_raw_scan(20000, 9), filter=None, density_adaptation=True)
+
+
+def test_radius_outlier_removal(engine):
+    """``filter: radius_outlier_removal`` (smartqsm.py:899-902): counts inside one ring of bricks (r < 8 cm) and beyond it
+    (r = 10 cm probes the hash for the second ring)."""
+    raw = make_raw_scan(30000, 14)
+    st, _ = _check(engine, raw, filter="radius_outlier_removal", nb_points=6, radius=0.03)
+    assert st["n_kept"] < st["n_voxel"]
+    _check(engine, make_raw_scan(8000, 15, leaf_on=True), filter="radius_outlier_removal", nb_points=40, radius=0.1,
+           density_adaptation=False)
 
 
 def test_isolated_points_use_the_ring_search(engine):
@@ -109,7 +125,7 @@ def test_errors_and_determinism(engine):
         engine.prepare_cloud(np.array([[1.0, np.nan, 3.0], [0.0, 0.0, 0.0]]))
     with pytest.raises(NotImplementedError):
         from smartqsm_b200.preprocess import prepare_cloud
-        prepare_cloud(np.zeros((4, 3)), filter="radius_outlier_removal", engine=engine)
+        prepare_cloud(np.zeros((4, 3)), filter="bilateral", engine=engine)
     raw = make_raw_scan(50000, 13, leaf_on=True)
     engine.prepare_cloud(raw)
     p1 = engine.prepared_points()

@@ -51,6 +51,17 @@ def test_statistical_outlier_matches_brute_force():
     assert 0 < len(keep) < len(p)
 
 
+def test_radius_outlier_matches_brute_force():
+    rng = np.random.default_rng(4)
+    p = np.concatenate([rng.normal(0, 0.05, (500, 3)), rng.uniform(-2, 2, (20, 3))])
+    p[1] = p[0] + np.array([0.125, 0.0, 0.0])                  # a pair at exactly r: the ball is open, it does not count
+    keep, cnt = OP.remove_radius_outlier(p, 5, 0.125)
+    d2 = ((p[:, None, :] - p[None, :, :]) ** 2).sum(-1)
+    cnt_b = (d2 < 0.125 * 0.125).sum(axis=1)                   # itself included
+    assert np.array_equal(cnt, cnt_b)
+    assert np.array_equal(keep, np.nonzero(cnt_b > 5)[0]) and 0 < len(keep) < len(p)
+
+
 def test_density_scale_matches_brute_force():
     rng = np.random.default_rng(2)
     p = rng.uniform(0, 1, (700, 3))
