@@ -52,11 +52,12 @@ __global__ void __launch_bounds__(256) k_conv(ConvArgs a) {
     if (BN) {
         for (int i = t; i < 2 * CI; i += 256) sbn[i] = a.bn[i];
     }
-    float acc[RPT][CPT];
+    // accumulators as float2 pairs: fma.rn.f32x2 (__ffma2_rn, sm_100) issues two exact fp32 FMAs per instruction slot
+    float2 acc2[RPT][CPT / 2];
     #pragma unroll
     for (int j = 0; j < RPT; ++j)
         #pragma unroll
-        for (int c = 0; c < CPT; ++c) acc[j][c] = 0.0f;
+        for (int c = 0; c < CPT / 2; ++c) acc2[j][c] = make_float2(0.0f, 0.0f);
 
     for (int k0 = 0; k0 < KV; k0 += a.kc) {
         const int kn = min(a.kc, KV - k0);
@@ -109,13 +110,13 @@ __global__ void __launch_bounds__(256) k_conv(ConvArgs a) {
                     #pragma unroll
                     for (int q = 0; q < CPT / 4; ++q) {
                         const float4 wv = *reinterpret_cast<const float4*>(wrow + 4 * q);
+                        const float2 w01 = make_float2(wv.x, wv.y), w23 = make_float2(wv.z, wv.w);
                         #pragma unroll
                         for (int j = 0; j < RPT; ++j) {
                             const float s = comp4(v[j], cc);
-                            acc[j][4 * q + 0] = fmaf(s, wv.x, acc[j][4 * q + 0]);
-                            acc[j][4 * q + 1] = fmaf(s, wv.y, acc[j][4 * q + 1]);
-                            acc[j][4 * q + 2] = fmaf(s, wv.z, acc[j][4 * q + 2]);
-                            acc[j][4 * q + 3] = fmaf(s, wv.w, acc[j][4 * q + 3]);
+                            const float2 ss = make_float2(s, s);
+                            acc2[j][2 * q + 0] = __ffma2_rn(ss, w01, acc2[j][2 * q + 0]);
+                            acc2[j][2 * q + 1] = __ffma2_rn(ss, w23, acc2[j][2 * q + 1]);
                         }
                     }
                 }
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(256) k_conv(ConvArgs a) {
         const bool take_src = a.sel_flag && a.sel_flag[row] == 0;
         #pragma unroll
         for (int q = 0; q < CPT / 4; ++q) {
-            float4 r = make_float4(acc[j][4 * q], acc[j][4 * q + 1], acc[j][4 * q + 2], acc[j][4 * q + 3]);
+            float4 r = make_float4(acc2[j][2 * q].x, acc2[j][2 * q].y, acc2[j][2 * q + 1].x, acc2[j][2 * q + 1].y);
             if (a.res) {
                 float4 e = *reinterpret_cast<const float4*>(a.res + o + 4 * q);
                 r.x += e.x; r.y += e.y; r.z += e.z; r.w += e.w;
