@@ -195,9 +195,9 @@ __global__ void __launch_bounds__(256) k_upconv(const float* __restrict__ in, co
         for (int i = t; i < P; i += 256) {
             const int row = tile0 + (int)lists[kk * T + i];
             const float4* src = reinterpret_cast<const float4*>(in + (size_t)parent[row] * CI);
-            float acc[CO];
+            float2 acc[CO / 2];                          // float2 pairs: fma.rn.f32x2, two exact fp32 FMAs per issue slot
             #pragma unroll
-            for (int c = 0; c < CO; ++c) acc[c] = 0.0f;
+            for (int c = 0; c < CO / 2; ++c) acc[c] = make_float2(0.0f, 0.0f);
             #pragma unroll
             for (int c0 = 0; c0 < CI; c0 += 4) {
                 const float4 x = __ldg(src + c0 / 4);
@@ -205,20 +205,19 @@ __global__ void __launch_bounds__(256) k_upconv(const float* __restrict__ in, co
                 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
                     const float av = fmaxf(fmaf(v[cc], sbn[c0 + cc], sbn[CI + c0 + cc]), 0.0f);
+                    const float2 aa = make_float2(av, av);
                     const float* wrow = sw + (c0 + cc) * CO;
                     #pragma unroll
                     for (int q = 0; q < CO / 4; ++q) {
                         const float4 wv = *reinterpret_cast<const float4*>(wrow + 4 * q);
-                        acc[4 * q + 0] = fmaf(av, wv.x, acc[4 * q + 0]);
-                        acc[4 * q + 1] = fmaf(av, wv.y, acc[4 * q + 1]);
-                        acc[4 * q + 2] = fmaf(av, wv.z, acc[4 * q + 2]);
-                        acc[4 * q + 3] = fmaf(av, wv.w, acc[4 * q + 3]);
+                        acc[2 * q + 0] = __ffma2_rn(aa, make_float2(wv.x, wv.y), acc[2 * q + 0]);
+                        acc[2 * q + 1] = __ffma2_rn(aa, make_float2(wv.z, wv.w), acc[2 * q + 1]);
                     }
                 }
             }
             float4* dst = reinterpret_cast<float4*>(out + (size_t)row * CO);
             #pragma unroll
-            for (int c = 0; c < CO / 4; ++c) dst[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+            for (int c = 0; c < CO / 4; ++c) dst[c] = make_float4(acc[2 * c].x, acc[2 * c].y, acc[2 * c + 1].x, acc[2 * c + 1].y);
         }
     }
 }
