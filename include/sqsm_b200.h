@@ -142,7 +142,7 @@ int  sqsm_radius_graph_points(sqsm_handle h, const float* h_points_xyz, int64_t 
  * statistical_outlier_removal (:895-898) and radius_outlier_removal (:899-902, Open3D: more than nb_points points,
  * itself included, with squared distance < radius^2). */
 typedef struct SqsmPrepConfig {
-    double  voxel_down_size;      /* configs/*.yaml: voxel_down_size (0.01) */
+    double  voxel_down_size;      /* configs/<name>.yaml: voxel_down_size (0.01) */
     double  std_ratio;            /* kwargs_for_filter.std_ratio (4.0) */
     int32_t filter;               /* 0 = none, 1 = statistical_outlier_removal, 2 = radius_outlier_removal */
     int32_t nb_neighbors;         /* kwargs_for_filter.nb_neighbors (10); 1..32 */

@@ -54,7 +54,6 @@ struct TcArgs {
 };
 
 constexpr int kTcMaxStages = 6;       // shared-memory ring (A hi/lo + B hi/lo per stage), as many as fit 227 KB
-constexpr int kTcPrefetch = 3;        // chunks of gather loads in flight per producer thread (registers)
 // producer groups (template parameter GR): group g gathers chunks g, g+GR, ... (thread-level parallelism: one warp per SM
 // sub-partition cannot hide its own issue latencies).  Measured per C3 step: 3 groups beat 2 for the 16-channel sources
 // (16->16: 137 -> 124 ms, 32->16: 88 -> 81 ms) and lose for the wider ones (64->32: 71 -> 78 ms).
@@ -289,7 +288,7 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
                 fence_proxy_async();                    // cp.async wrote through the generic proxy; the MMA reads through the async proxy
                 tc_fence_after();
                 const uint32_t sA_hi = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-                const uint32_t sA_lo = sA_hi + A_BYTES, sB_hi = sA_lo + A_BYTES, sB_lo = sB_hi + B_BYTES;
+                const uint32_t sA_lo = sA_hi + A_BYTES, sB_hi = sA_lo + A_BYTES;        // W_lo rows follow W_hi at sB_hi + B_BYTES
                 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {        // 4 K steps of 8 tf32 (32 B) inside the 128 B swizzle span
                     const uint64_t ah = make_desc_sw128(sA_hi + ks * 32), bh = make_desc_sw128(sB_hi + ks * 32);
