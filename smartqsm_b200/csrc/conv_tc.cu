@@ -115,9 +115,9 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
     const uint32_t tmem_base = tmem_slot;
 
     if (warp < kTcProdWarps) {
-        // ===================== producers: gather -> TF32 hi/lo split -> swizzled smem tiles =====================
-        // One chunk = 8 float4 per thread.  kTcPrefetch chunks are kept in flight in registers so that the
-        // latency of the gather (L2 / HBM) overlaps with the stores of earlier chunks.
+        // ===================== producers: rulebook rows -> cp.async gather into the swizzled smem tiles =====================
+        // Nothing but rulebook entries passes through registers: the pre-split operands go global -> shared by LDGSTS and
+        // the stage's mbarrier counts their arrival.
         const int n_my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
         const int total = n_my_tiles * NCH;               // chunk sequence of this CTA
         const int grp = warp >> 2;                        // producer group
