@@ -211,6 +211,9 @@ int  sqsm_profile_families(sqsm_handle h, char* buf, int64_t capacity);   /* com
 int  sqsm_timer_start(sqsm_handle h);
 int  sqsm_timer_stop(sqsm_handle h, double* elapsed_ms);
 int  sqsm_launch_count(sqsm_handle h, int64_t* kernels_launched_since_create);
+/* sizeof() of the public structs as the library was compiled: 0 SqsmConfig, 1 SqsmIterStats, 2 SqsmPrepConfig,
+ * 3 SqsmPrepStats (-1 otherwise) - lets a binding verify its own declarations without a GPU. */
+int  sqsm_sizeof(int32_t which);
 
 #ifdef __cplusplus
 }

@@ -71,7 +71,7 @@ EXPORTS = [
     "sqsm_debug_batch_shapes", "sqsm_debug_level_tables", "sqsm_debug_canon_to_internal",
     "sqsm_debug_predictions", "sqsm_debug_features", "sqsm_profile_reset", "sqsm_profile_get",
     "sqsm_profile_enable", "sqsm_profile_families", "sqsm_timer_start", "sqsm_timer_stop", "sqsm_launch_count",
-    "sqsm_prepare_cloud_f64", "sqsm_prepared_size", "sqsm_get_prepared", "sqsm_set_points_prepared", "sqsm_debug_prepared",
+    "sqsm_prepare_cloud_f64", "sqsm_prepared_size", "sqsm_get_prepared", "sqsm_set_points_prepared", "sqsm_debug_prepared", "sqsm_sizeof",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -130,6 +130,7 @@ def load_library() -> C.CDLL:
         "sqsm_get_prepared": ([vp, vp], C.c_int),
         "sqsm_set_points_prepared": ([vp], C.c_int),
         "sqsm_debug_prepared": ([vp, vp, vp, vp], C.c_int),
+        "sqsm_sizeof": ([i32], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, name)

@@ -81,6 +81,16 @@ static double decimal_double(float v) {
 
 extern "C" int sqsm_abi_version(void) { return 1; }
 
+extern "C" int sqsm_sizeof(int32_t which) {
+    switch (which) {
+        case 0: return (int)sizeof(SqsmConfig);
+        case 1: return (int)sizeof(SqsmIterStats);
+        case 2: return (int)sizeof(SqsmPrepConfig);
+        case 3: return (int)sizeof(SqsmPrepStats);
+        default: return -1;
+    }
+}
+
 extern "C" const char* sqsm_last_error(sqsm_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 extern "C" int sqsm_create(const SqsmConfig* cfg, sqsm_handle* out) {

@@ -30,6 +30,10 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     from smartqsm_b200 import _lib
+    lib = _lib.load_library()                     # sizeof() as compiled into the library against the ctypes declarations
+    for which, struct in enumerate((_lib.SqsmConfig, _lib.SqsmIterStats, _lib.SqsmPrepConfig, _lib.SqsmPrepStats)):
+        assert lib.sqsm_sizeof(which) == ctypes.sizeof(struct), struct.__name__
+    assert lib.sqsm_sizeof(99) == -1
     assert ctypes.sizeof(_lib.SqsmConfig) == 16 * 4
     assert ctypes.sizeof(_lib.SqsmIterStats) == 14 * 8 + 8 + 4 * 4 + 5 * 4 + 4   # 14 int64, double, 4 int32, 5 float, tail pad
 
