@@ -45,13 +45,23 @@ void sort_pairs_u32(Ctx& cx, const uint32_t* d_kin, uint32_t* d_kout, const uint
     cx.launches += 2 * ((end_bit - begin_bit + 7) / 8) + 1;
 }
 
-void segmented_sort_u32(Ctx& cx, const uint32_t* d_in, uint32_t* d_out, int64_t n, int64_t n_segments, const int64_t* d_off) {
+struct OffsetMinusBase {
+    const int64_t* off; int64_t base;
+    __host__ __device__ __forceinline__ int64_t operator()(int64_t i) const { return off[i] - base; }
+};
+
+void segmented_sort_u32(Ctx& cx, const uint32_t* d_in, uint32_t* d_out, int64_t n, int64_t n_segments, const int64_t* d_off,
+                        int64_t base) {
     if (n <= 0 || n_segments <= 0) return;
     SQSM_CHECK(n < (1ll << 31) && n_segments < (1ll << 31), "segmented sort: more than 2^31 items");
+    // segment s of this call = [d_off[s] - base, d_off[s + 1] - base): the offsets stay 64-bit and global, so a caller can
+    // sort a list of more than 2^31 items chunk by chunk
+    cub::CountingInputIterator<int64_t> cnt(0);
+    cub::TransformInputIterator<int64_t, OffsetMinusBase, cub::CountingInputIterator<int64_t>> beg(cnt, OffsetMinusBase{d_off, base});
     size_t tb = 0;
-    SQSM_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, tb, d_in, d_out, (int)n, (int)n_segments, d_off, d_off + 1, cx.st));
+    SQSM_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, tb, d_in, d_out, (int)n, (int)n_segments, beg, beg + 1, cx.st));
     DBuf<uint8_t> tmp((int64_t)tb + 16, cx.st);
-    SQSM_CUDA(cub::DeviceSegmentedSort::SortKeys(tmp.p, tb, d_in, d_out, (int)n, (int)n_segments, d_off, d_off + 1, cx.st));
+    SQSM_CUDA(cub::DeviceSegmentedSort::SortKeys(tmp.p, tb, d_in, d_out, (int)n, (int)n_segments, beg, beg + 1, cx.st));
     cx.launches += 3;
 }
 

@@ -95,7 +95,8 @@ void exclusive_scan_i64(Ctx& cx, const int64_t* d_in, int64_t* d_out, int64_t n)
 void sort_keys_u64(Ctx& cx, const uint64_t* d_in, uint64_t* d_out, int64_t n, int begin_bit, int end_bit);
 void sort_pairs_u32(Ctx& cx, const uint32_t* d_kin, uint32_t* d_kout, const uint32_t* d_vin, uint32_t* d_vout,
                     int64_t n, int begin_bit, int end_bit);
-// ascending sort of the keys inside every segment [d_off[s], d_off[s + 1]) (cub::DeviceSegmentedSort)
-void segmented_sort_u32(Ctx& cx, const uint32_t* d_in, uint32_t* d_out, int64_t n, int64_t n_segments, const int64_t* d_off);
+// ascending sort of the keys inside every segment [d_off[s] - base, d_off[s + 1] - base) (cub::DeviceSegmentedSort)
+void segmented_sort_u32(Ctx& cx, const uint32_t* d_in, uint32_t* d_out, int64_t n, int64_t n_segments, const int64_t* d_off,
+                        int64_t base = 0);
 
 }  // namespace sqsm

@@ -328,6 +328,10 @@ std::vector<float> make_tc_weight_image_f16(const float* w_kcico, int kv, int ci
 std::vector<float> make_tma_weight_image(const float* w_kcico, int kv, int ci, int co, int cs, int g);   // conv_tma.cu
 bool conv_tma_supported(int ci, int co, int kv, bool cat);
 int tma_group(int cs, int kv);
+std::vector<float> make_up_weight_image_f16(const float* w_kcico, int ci, int co);   // upconv_tc.cu
+bool upconv_tc(Ctx& cx, int ci, int co, const void* in_hi, const void* in_lo, const int32_t* child, const int32_t* parent,
+               const float* wimg, float* out, void* raw_hi, void* raw_lo, void* act_hi, void* act_lo, const float* act_alpha,
+               const float* act_beta, int* range_flag, int64_t n_coarse, int64_t n_fine);
 void act_split_rows(Ctx& cx, const float* in, const float* bn, int c, int bn_off, int bn_stride, int64_t n, void* out, int* range_flag);
 bool conv_tma(Ctx& cx, int ci, int co, int kv, bool cat, const void* splitA, const void* splitB, const int32_t* nbr, const float* wimg,
               const float* res, const float* sel_src, const uint8_t* sel_flag, float* out, int64_t n_out, int64_t n_in);
@@ -357,7 +361,7 @@ static void fold_bn(const std::map<std::string, std::vector<float>>& st, const s
 
 void net_upload(Ctx& cx, NetWeights& nw, const std::map<std::string, std::vector<float>>& st, bool down_flip) {
     std::vector<float> blob;
-    struct Pending { std::string name; size_t w_off, bn_off, img_off, img16_off; bool has_bn, has_img; int ci, co, kv; size_t tma_off = 0; bool has_tma = false; };
+    struct Pending { std::string name; size_t w_off, bn_off, img_off, img16_off; bool has_bn, has_img; int ci, co, kv; size_t tma_off = 0; bool has_tma = false; size_t up_off = 0; bool has_up = false; };
     std::vector<Pending> pend;
     auto add_conv = [&](const std::string& name, const std::string& wkey, const std::string& bnkey, int ci, int co, int kv,
                         int ci_pad, bool flip, bool cat = false) {
@@ -395,6 +399,13 @@ void net_upload(Ctx& cx, NetWeights& nw, const std::map<std::string, std::vector
             p.has_tma = true;
             blob.insert(blob.end(), img.begin(), img.end());
         }
+        if (name.size() > 3 && name.compare(name.size() - 3, 3, ".up") == 0) {      // inverse convolution as a dense GEMM (upconv_tc.cu)
+            std::vector<float> img = make_up_weight_image_f16(&blob[p.w_off], ci_pad, co);
+            while (blob.size() % 64) blob.push_back(0.0f);
+            p.up_off = blob.size();
+            p.has_up = true;
+            blob.insert(blob.end(), img.begin(), img.end());
+        }
         pend.push_back(p);
     };
     add_conv("input", "input_conv.0.weight", "", 3, kPlanes[0], 27, 4, false);
@@ -428,6 +439,7 @@ void net_upload(Ctx& cx, NetWeights& nw, const std::map<std::string, std::vector
         c.wimg = p.has_img ? nw.blob.p + p.img_off : nullptr;
         c.wimg16 = p.has_img ? nw.blob.p + p.img16_off : nullptr;
         c.wimg_tma = p.has_tma ? nw.blob.p + p.tma_off : nullptr;
+        c.wimg_up = p.has_up ? nw.blob.p + p.up_off : nullptr;
         nw.conv[p.name] = c;
     }
     // heads (App. A #48-51)
@@ -498,17 +510,21 @@ struct FusedSplit {
 
 static bool tc_f16_layer(const NetWeights& nw, const ConvW& w) { return nw.mode == 3 && w.wimg16 && w.co >= nw.tc_min_co; }
 
+// tensor cores from tc_min_co output channels up, plus the level-0 decoder conv on the concatenated 16 channels
+// (16 -> 8, 27 offsets: 51 vs 66 ms per C3 step on FFMA; the other 8-channel layers are faster on FFMA)
+static bool layer_uses_tc(const NetWeights& nw, const ConvW& w, bool cat) {
+    return nw.mode != 0 && w.wimg && (w.co >= nw.tc_min_co || (nw.mode >= 3 && cat && w.ci == 16 && w.co == 8 && w.kv == 27));
+}
+
 static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, bool cat, const float* inA, const float* inB,
                      const int32_t* nbr, float* out, int64_t n_out, int64_t n_in, const float* res = nullptr,
                      const float* sel_src = nullptr, const uint8_t* sel_flag = nullptr, const FusedSplit* consume = nullptr,
-                     FusedSplit* produce = nullptr, const char* consumer = nullptr, bool need_fp32 = true) {
+                     FusedSplit* produce = nullptr, const char* consumer = nullptr, bool need_fp32 = true,
+                     const FusedSplit* consumeB = nullptr) {
     const ConvW& w = nw.conv.at(name);
     if (produce) produce->ready = false;
     if (n_out <= 0) return;
-    // tensor cores from tc_min_co output channels up, plus the level-0 decoder conv on the concatenated 16 channels
-    // (16 -> 8, 27 offsets: 51 vs 66 ms per C3 step on FFMA; the other 8-channel layers are faster on FFMA)
-    const bool use_tc = nw.mode != 0 && w.wimg &&
-                        (w.co >= nw.tc_min_co || (nw.mode >= 3 && cat && w.ci == 16 && w.co == 8 && w.kv == 27));
+    const bool use_tc = layer_uses_tc(nw, w, cat);
     // per-kernel scope: algorithmic bytes of SURVEY 8(d): features in + out, rulebook entries, residual re-read
     char fam[64];
     snprintf(fam, sizeof(fam), "conv_%s_ci%d_co%d_k%d", use_tc ? "tc" : "ffma", w.ci, w.co, w.kv);
@@ -542,31 +558,37 @@ static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, boo
         // FP16 operands take half the space of TF32 ones: allocate in float units either way
         const int64_t elems = f16 ? (n_in * ca + 1) / 2 : n_in * ca;
         DBuf<float> a_hi, a_lo, b_hi, b_lo;
-        const float *pa_hi, *pa_lo;
-        if (consume && consume->ready && f16 && !cat) {          // the producer already wrote this layer's operands
-            pa_hi = consume->hi.p;
-            pa_lo = consume->lo.p;
-        } else {
-            a_hi.alloc(elems, cx.st);
-            if (precise) a_lo.alloc(elems, cx.st);
-            ProfScope pa(cx, "act_split", (double)n_in * w.ci * (f16 ? 8.0 : 4.0 * (precise ? 3 : 2)), 0.0);
-            if (f16) act_split_f16(cx, inA, w.bn, ca, 0, w.ci, n_in, a_hi.p, a_lo.p, nw.range_flag);
-            else act_split(cx, inA, w.bn, ca, 0, w.ci, n_in, a_hi.p, a_lo.p);
-            if (cat) {
+        const float *pa_hi, *pa_lo, *pb_hi = nullptr, *pb_lo = nullptr;
+        // operands already written by the producer of the tensor (FusedSplit): first source / second source of a concat
+        const bool preA = consume && consume->ready && f16;
+        const bool preB = cat && consumeB && consumeB->ready && f16;
+        if (preA) { pa_hi = consume->hi.p; pa_lo = consume->lo.p; }
+        if (preB) { pb_hi = consumeB->hi.p; pb_lo = consumeB->lo.p; }
+        if (!preA || (cat && !preB)) {
+            ProfScope pa(cx, "act_split", (double)n_in * ca * ((preA ? 0 : 1) + (cat && !preB ? 1 : 0)) * (f16 ? 8.0 : 4.0 * (precise ? 3 : 2)), 0.0);
+            if (!preA) {
+                a_hi.alloc(elems, cx.st);
+                if (precise) a_lo.alloc(elems, cx.st);
+                if (f16) act_split_f16(cx, inA, w.bn, ca, 0, w.ci, n_in, a_hi.p, a_lo.p, nw.range_flag);
+                else act_split(cx, inA, w.bn, ca, 0, w.ci, n_in, a_hi.p, a_lo.p);
+                pa_hi = a_hi.p;
+                pa_lo = a_lo.p;
+            }
+            if (cat && !preB) {
                 b_hi.alloc(elems, cx.st);
                 if (precise) b_lo.alloc(elems, cx.st);
                 if (f16) act_split_f16(cx, inB, w.bn, ca, ca, w.ci, n_in, b_hi.p, b_lo.p, nw.range_flag);
                 else act_split(cx, inB, w.bn, ca, ca, w.ci, n_in, b_hi.p, b_lo.p);
+                pb_hi = b_hi.p;
+                pb_lo = b_lo.p;
             }
-            pa_hi = a_hi.p;
-            pa_lo = a_lo.p;
         }
         // fused split for the consumer: only between two FP16 tensor-core layers, and the consumer must own a BatchNorm
         void *o_hi = nullptr, *o_lo = nullptr;
         const float* o_bn = nullptr;
         if (produce && consumer && f16 && nw.mode == 3) {
             const ConvW& wc = nw.conv.at(consumer);
-            if (tc_f16_layer(nw, wc) && wc.bn && wc.ci == w.co) {
+            if ((tc_f16_layer(nw, wc) || wc.wimg_up) && wc.bn && wc.ci == w.co) {
                 const int64_t oe = (n_out * w.co + 1) / 2;
                 produce->hi.alloc(oe, cx.st);
                 produce->lo.alloc(oe, cx.st);
@@ -576,7 +598,7 @@ static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, boo
         }
         float* o_f32 = (o_hi && !need_fp32) ? nullptr : out;
         ProfScope ps(cx, fam, alg_bytes, 0.0);
-        if (conv_tc(cx, w.ci, w.co, w.kv, cat, pa_hi, b_hi.p, pa_lo, b_lo.p, nbr, f16 ? w.wimg16 : w.wimg, res, sel_src, sel_flag,
+        if (conv_tc(cx, w.ci, w.co, w.kv, cat, pa_hi, pb_hi, pa_lo, pb_lo, nbr, f16 ? w.wimg16 : w.wimg, res, sel_src, sel_flag,
                     o_f32, n_out, precise, f16, o_hi, o_lo, o_bn, nw.range_flag))
             return;
         if (produce) produce->ready = false;
@@ -605,6 +627,8 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
     cudaStream_t st = cx.st;
     SQSM_CHECK(nw.ready, "weights not finalised");
     DBuf<float> enc[kLevels], tmp[kLevels];
+    const bool up_on_tc = nw.mode == 3 && getenv("SQSM_UPCONV_FFMA") == nullptr;   // inverse convolutions as dense GEMMs (upconv_tc.cu)
+    FusedSplit sp_cur;                       // operands of the next inverse convolution, written by the producer of `cur`
     // ---- encoder (smart_tree_xx.py:65-66, sparse_module.py:101-112)
     const int64_t n0 = lv[0].n;
     DBuf<float> cur_in(n0 * 8, st);
@@ -626,7 +650,11 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
             const std::string nb = L + ".blk.b";
             conv_any(cx, nw, L + ".blk.a", false, cur_in.p, nullptr, lv[l].nbr.p, tmp[l].p, n, n, nullptr, nullptr, nullptr, nullptr,
                      &sp_mid, nb.c_str(), /*need_fp32=*/false);
-            conv_any(cx, nw, nb, false, tmp[l].p, nullptr, lv[l].nbr.p, enc[l].p, n, n, cur_in.p, nullptr, nullptr, &sp_mid);
+            // the deepest level feeds the inverse convolution only: its epilogue writes that layer's operands
+            const bool deepest = (l == n_levels - 1) && l > 0 && up_on_tc;
+            const std::string upn = "L" + std::to_string(l - 1) + ".up";
+            conv_any(cx, nw, nb, false, tmp[l].p, nullptr, lv[l].nbr.p, enc[l].p, n, n, cur_in.p, nullptr, nullptr, &sp_mid,
+                     deepest ? &sp_cur : nullptr, deepest ? upn.c_str() : nullptr, /*need_fp32=*/keep || !deepest);
         }
         if (keep) keep_copy(cx, fb, "enc" + std::to_string(l), enc[l].p, n, c, l);
         if (l + 1 < n_levels) {
@@ -642,27 +670,57 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
     // ---- decoder (sparse_module.py:112-116)
     DBuf<float> cur = std::move(enc[n_levels - 1]);
     for (int l = n_levels - 2; l >= 0; --l) {
-        const int64_t n = lv[l].n;
-        const int c = kPlanes[l];
+        const int64_t n = lv[l].n, nc = lv[l + 1].n;
+        const int c = kPlanes[l], cn = kPlanes[l + 1];
         const std::string L = "L" + std::to_string(l);
-        DBuf<float> up(n * c, st), res(n * c, st), out(n * c, st);
+        const ConvW& wu = nw.conv.at(L + ".up");
+        const ConvW& wi = nw.conv.at(L + ".tail.i");
+        const ConvW& wa = nw.conv.at(L + ".tail.a");
+        DBuf<float> up, res(n * c, st), out(n * c, st);
+        FusedSplit up_raw, up_act;           // the decoder half of the concat as operands of tail.i (raw) and tail.a (BN + ReLU)
         {
-            ProfScope pt(cx, "down_up", 4.0 * (lv[l + 1].n * kPlanes[l + 1] + n * c) + 4.0 * n,
-                         2.0 * (double)n * c * kPlanes[l + 1]);
-            const ConvW& wu = nw.conv.at(L + ".up");
-            if (l == 0) launch_upconv<16, 8>(cx, wu, cur.p, lv[l].parent.p, lv[l].koff.p, up.p, n);
-            else if (l == 1) launch_upconv<32, 16>(cx, wu, cur.p, lv[l].parent.p, lv[l].koff.p, up.p, n);
-            else launch_upconv<64, 32>(cx, wu, cur.p, lv[l].parent.p, lv[l].koff.p, up.p, n);
+            ProfScope pt(cx, "down_up", 4.0 * (nc * cn + n * c) + 4.0 * n, 2.0 * (double)n * c * cn);
+            if (up_on_tc && wu.wimg_up) {
+                if (!sp_cur.ready) {                          // producer could not fuse the split (FFMA layer): one pass
+                    const int64_t e = (nc * cn + 1) / 2;
+                    sp_cur.hi.alloc(e, st);
+                    sp_cur.lo.alloc(e, st);
+                    ProfScope pa(cx, "act_split", (double)nc * cn * 8.0, 0.0);
+                    act_split_f16(cx, cur.p, wu.bn, cn, 0, cn, nc, sp_cur.hi.p, sp_cur.lo.p, nw.range_flag);
+                }
+                const bool i_tc = layer_uses_tc(nw, wi, true) && nw.mode == 3, a_tc = layer_uses_tc(nw, wa, true) && nw.mode == 3;
+                const int64_t e = (n * c + 1) / 2;
+                if (i_tc) { up_raw.hi.alloc(e, st); up_raw.lo.alloc(e, st); up_raw.ready = true; }
+                if (a_tc) { up_act.hi.alloc(e, st); up_act.lo.alloc(e, st); up_act.ready = true; }
+                if (!i_tc || !a_tc) up.alloc(n * c, st);      // a float32 consumer remains
+                char fam[64];
+                snprintf(fam, sizeof(fam), "conv_tc_up_ci%d_co%d", cn, c);
+                ProfScope ps(cx, fam, 4.0 * ((double)nc * cn + (double)n * c) + 4.0 * 8 * (double)nc, 0.0);
+                if (!upconv_tc(cx, cn, c, sp_cur.hi.p, sp_cur.lo.p, lv[l].child.p, lv[l].parent.p, wu.wimg_up, up.p, up_raw.hi.p,
+                               up_raw.lo.p, up_act.hi.p, up_act.lo.p, wa.bn + c, wa.bn + 2 * c + c, nw.range_flag, nc, n))
+                    throw CudaError("upconv_tc: unsupported shape");
+            } else {
+                up.alloc(n * c, st);
+                if (l == 0) launch_upconv<16, 8>(cx, wu, cur.p, lv[l].parent.p, lv[l].koff.p, up.p, n);
+                else if (l == 1) launch_upconv<32, 16>(cx, wu, cur.p, lv[l].parent.p, lv[l].koff.p, up.p, n);
+                else launch_upconv<64, 32>(cx, wu, cur.p, lv[l].parent.p, lv[l].koff.p, up.p, n);
+            }
+            sp_cur = FusedSplit();
         }
         {   // blocks_tail on cat(enc, up); rows of batches that did not descend keep `enc`
             ProfScope pt(cx, lvl_family(l), 4.0 * n * (2 * c + c) * 2 + 4.0 * n * (c + c) + 2.0 * 4.0 * 27 * n + 4.0 * n * c,
                          2.0 * (double)lv[l].pairs * (2 * c * c + c * c) + 2.0 * (double)n * 2 * c * c);
-            conv_any(cx, nw, L + ".tail.i", true, enc[l].p, up.p, nullptr, res.p, n, n);
+            conv_any(cx, nw, L + ".tail.i", true, enc[l].p, up.p, nullptr, res.p, n, n, nullptr, nullptr, nullptr, nullptr, nullptr,
+                     nullptr, true, &up_raw);
             FusedSplit sp_mid;
             const std::string nb = L + ".tail.b";
             conv_any(cx, nw, L + ".tail.a", true, enc[l].p, up.p, lv[l].nbr.p, tmp[l].p, n, n, nullptr, nullptr, nullptr, nullptr,
-                     &sp_mid, nb.c_str(), /*need_fp32=*/false);
-            conv_any(cx, nw, nb, false, tmp[l].p, nullptr, lv[l].nbr.p, out.p, n, n, res.p, enc[l].p, lv[l].row_desc.p, &sp_mid);
+                     &sp_mid, nb.c_str(), /*need_fp32=*/false, &up_act);
+            // the level's output feeds the next inverse convolution only (levels >= 1): fused operands, no float32 copy
+            const bool feeds_up = l > 0 && up_on_tc;
+            const std::string upn = "L" + std::to_string(l - 1) + ".up";
+            conv_any(cx, nw, nb, false, tmp[l].p, nullptr, lv[l].nbr.p, out.p, n, n, res.p, enc[l].p, lv[l].row_desc.p, &sp_mid,
+                     feeds_up ? &sp_cur : nullptr, feeds_up ? upn.c_str() : nullptr, /*need_fp32=*/keep || !feeds_up);
         }
         if (keep) keep_copy(cx, fb, "dec" + std::to_string(l), out.p, n, c, l);
         cur = std::move(out);

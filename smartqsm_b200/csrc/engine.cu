@@ -44,6 +44,7 @@ struct sqsm_engine {
     cudaEvent_t tm_a = nullptr, tm_b = nullptr; // sqsm_timer_start / stop
     SkeletalResult sk;
     bool sk_valid = false;
+    double sk_voxel = 0.0;          // voxel_size_for_downsampling the cached sample was made with
     DBuf<int64_t> edges;            // cached radius graph of `sk`
     int64_t n_edges = 0;
     double edges_r = -1.0;
@@ -136,9 +137,14 @@ extern "C" void sqsm_destroy(sqsm_handle h) {
     cudaSetDevice(h->cfg.device);
     cudaStream_t st = h->cx.st;
     cudaStreamSynchronize(st);
+    const int dev = h->cfg.device;
     delete h;                                               // DBufs free on the stream
     cudaStreamSynchronize(st);
     cudaStreamDestroy(st);
+    // hand the cached blocks of the (process-wide) default pool back to the driver: the reference pipeline and torch
+    // keep running in the same process after the engine is gone
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
 }
 
 extern "C" int sqsm_set_weight(sqsm_handle h, const char* name, const float* data, int64_t n) {
@@ -447,11 +453,15 @@ static void step_begin(sqsm_engine* h, int shard, int n_shards, SqsmIterStats& s
         }
         s0 = s1;
     }
-    if (h->nw.mode == 3) {
+    if (h->nw.mode == 3 || h->nw.mode == 4) {
         int flag = 0;
         SQSM_CUDA(cudaMemcpyAsync(&flag, h->nw.range_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
         SQSM_CUDA(cudaStreamSynchronize(st));
-        SQSM_CHECK(flag == 0, "an activation exceeded the FP16 range in conv_mode 4 (3xFP16); use conv_mode 2 (3xTF32)");
+        if (flag != 0) {
+            SQSM_CUDA(cudaMemsetAsync(h->nw.range_flag, 0, sizeof(int), st));    // the next step starts clean
+            h->cand_valid = false;
+            SQSM_CHECK(false, "an activation exceeded the FP16 range in conv_mode 4/5 (3xFP16); use conv_mode 2 (3xTF32)");
+        }
     }
     s.n_out = out_base;
     if (Trace::enabled()) fprintf(stderr, "[trace] ---- end of passes, n_out %lld\n", (long long)out_base);
@@ -592,11 +602,14 @@ extern "C" int sqsm_skeletal_sample(sqsm_handle h, double voxel, int64_t* m, int
     SQSM_API_BEGIN(h)
     SQSM_CHECK(h->n > 0 && m, "no state");
     cudaStream_t st = h->cx.st;
-    if (!h->sk_valid) {
+    SQSM_CHECK(voxel > 0.0, "voxel_size_for_downsampling must be positive");
+    if (!h->sk_valid || h->sk_voxel != voxel) {              // cached per (state, voxel): the binding asks twice (size, then data)
         ProfScope ps(h->cx, "skeletal", (double)h->n * (24.0 + 4.0), 0.0);
+        h->sk_valid = false;
+        h->edges_r = -1.0;
         skeletal_sample(h->cx, h->P.p, h->D.p, h->n, voxel, h->sk);
         h->sk_valid = true;
-        h->edges_r = -1.0;
+        h->sk_voxel = voxel;
     }
     *m = h->sk.m;
     if (ids) SQSM_CUDA(cudaMemcpyAsync(ids, h->sk.ids.p, sizeof(int64_t) * h->sk.m, cudaMemcpyDeviceToHost, st));

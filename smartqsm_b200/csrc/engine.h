@@ -56,6 +56,7 @@ struct ConvW {                          // one convolution, device resident
     float* wimg = nullptr;              // tensor-core weight image, TF32 hi/lo (conv_tc.cu) or null
     float* wimg16 = nullptr;            // tensor-core weight image, FP16 hi/lo
     float* wimg_tma = nullptr;          // weight image of the TMA-gather kernel (conv_tma.cu) or null
+    float* wimg_up = nullptr;           // inverse convolutions: FP16 image of the dense [ci][8*co] GEMM (upconv_tc.cu)
 };
 
 struct HeadW {                          // output_layer BN + both MLP heads; index 0 = offset, 1 = regression

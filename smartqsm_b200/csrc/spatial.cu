@@ -550,20 +550,23 @@ __global__ void __launch_bounds__(256) k_cell_count(const int32_t* __restrict__ 
     if (i < n && ent_brick[i] >= 0) atomicAdd(&cnt[ent_brick[i]], 1);
 }
 
-// mode 0: count neighbours j > i within r; mode 1: write them at off[i]
+// mode 0: count neighbours j > i within r; mode 1: write those of the nodes i in [i_lo, i_hi) at off[i] - off[i_lo]
+// (the edge list of a big cloud is produced in node-range chunks of < 2^31 edges, see radius_graph)
 template <int MODE>
 __global__ void __launch_bounds__(256) k_radius_pairs(const float* __restrict__ P, const uint32_t* __restrict__ order,
                                                       const uint32_t* __restrict__ cell_of, int64_t n,
                                                       const int32_t* __restrict__ bnbr, const int32_t* __restrict__ cstart,
                                                       double r2, int32_t* __restrict__ cnt, const int64_t* __restrict__ off,
-                                                      uint32_t* __restrict__ ebuf_i, uint32_t* __restrict__ ebuf_j) {
+                                                      uint32_t i_lo, uint32_t i_hi, uint32_t* __restrict__ ebuf_i,
+                                                      uint32_t* __restrict__ ebuf_j) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const uint32_t i = order[s];
+    if (MODE == 1 && (i < i_lo || i >= i_hi)) return;
     const int cell = (int)cell_of[s];
     const double x = (double)P[3 * (size_t)i], y = (double)P[3 * (size_t)i + 1], z = (double)P[3 * (size_t)i + 2];
     int c = 0;
-    int64_t o = (MODE == 1) ? off[i] : 0;
+    int64_t o = (MODE == 1) ? off[i] - off[i_lo] : 0;
     for (int nb = 0; nb < 27; ++nb) {
         int id = bnbr[(size_t)cell * 32 + nb];
         if (id < 0) continue;
@@ -582,11 +585,26 @@ __global__ void __launch_bounds__(256) k_radius_pairs(const float* __restrict__ 
     if (MODE == 0) cnt[i] = c;
 }
 
+// first node whose edge offset reaches k * budget, k = 0 .. n_chunks (chunk boundaries of the edge list)
+__global__ void k_chunk_bounds(const int64_t* __restrict__ off, int64_t m, int64_t budget, int n_bounds, int64_t* __restrict__ bounds) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_bounds) return;
+    const int64_t target = (int64_t)k * budget;
+    int64_t lo = 0, hi = m;                                   // first i in [0, m] with off[i] >= target
+    while (lo < hi) { int64_t mid = (lo + hi) / 2; if (off[mid] < target) lo = mid + 1; else hi = mid; }
+    bounds[k] = lo;
+}
+
 // (i, sorted j) 32-bit keys -> the int64 [E][2] edge list of the ABI; fully coalesced
 __global__ void __launch_bounds__(256) k_edges_expand(const uint32_t* __restrict__ ei, const uint32_t* __restrict__ ej, int64_t n,
                                                       longlong2* __restrict__ edges) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < n) edges[e] = make_longlong2((long long)ei[e], (long long)ej[e]);
+}
+
+__global__ void k_gather_i64(const int64_t* __restrict__ src, const int64_t* __restrict__ idx, int n, int64_t* __restrict__ dst) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) dst[k] = src[idx[k]];
 }
 
 __global__ void __launch_bounds__(256) k_iota_u32(uint32_t* __restrict__ a, int64_t n) {
@@ -603,7 +621,7 @@ void radius_graph(Ctx& cx, const float* d_pts, int64_t m, double r, DBuf<int64_t
     cudaStream_t st = cx.st;
     *n_edges = 0;
     if (m <= 1) return;
-    SQSM_CHECK(r > 0 && m < (1ll << 31), "radius graph: bad arguments");
+    SQSM_CHECK(r > 0 && m < (1ll << 31), "radius graph: bad arguments (at most 2^31 - 1 nodes)");
     double mn[3], mx[3];
     cloud_bounds(cx, d_pts, m, mn, mx);
     GridParams g;
@@ -644,7 +662,7 @@ void radius_graph(Ctx& cx, const float* d_pts, int64_t m, double r, DBuf<int64_t
     SQSM_CUDA(cudaMemsetAsync(cnt.p + m, 0, sizeof(int32_t), st));
     const double r2 = r * r;
     k_radius_pairs<0><<<div_up(m, 256), 256, 0, st>>>(d_pts, order.p, cell_sorted.p, m, map.bnbr.p, cstart.p, r2, cnt.p,
-                                                      nullptr, nullptr, nullptr);
+                                                      nullptr, 0u, 0u, nullptr, nullptr);
     DBuf<int64_t> cnt64(m + 1, st), off(m + 1, st);
     k_i32_to_i64<<<div_up(m + 1, 256), 256, 0, st>>>(cnt.p, cnt64.p, m + 1);
     cx.launches += 2;
@@ -654,17 +672,57 @@ void radius_graph(Ctx& cx, const float* d_pts, int64_t m, double r, DBuf<int64_t
     SQSM_CUDA(cudaStreamSynchronize(st));
     *n_edges = E;
     if (E == 0) return;
+    cnt.release();
+    cnt64.release();
     // fill (i, j) as 32-bit keys, sort j ascending inside every node's segment (the merged edge list is lexicographic,
-    // :158) with a segmented sort - no quadratic worst case for dense clusters - then expand to the int64 pairs of the ABI
-    SQSM_CHECK(E < (1ll << 31), "radius graph: more than 2^31 edges");
-    DBuf<uint32_t> ebuf_i(E, st), ebuf_j(E, st), ebuf_s(E, st);
-    k_radius_pairs<1><<<div_up(m, 256), 256, 0, st>>>(d_pts, order.p, cell_sorted.p, m, map.bnbr.p, cstart.p, r2, nullptr,
-                                                      off.p, ebuf_i.p, ebuf_j.p);
-    segmented_sort_u32(cx, ebuf_j.p, ebuf_s.p, E, m, off.p);
-    ebuf_j.release();
+    // :158) with a segmented sort - no quadratic worst case for dense clusters - then expand to the int64 pairs of the ABI.
+    // The list is produced in chunks of whole nodes with at most `budget` edges each (64-bit offsets throughout), so
+    // neither the 32-bit item count of the segmented sort nor the scratch buffers limit E: a 200 M-point scan has
+    // ~2.5 G edges.  A node with more than `budget` neighbours gets a chunk of its own.
+    const char* env_budget = getenv("SQSM_EDGE_CHUNK");
+    const int64_t budget = env_budget ? atoll(env_budget) : (1ll << 30);
+    SQSM_CHECK(budget > 0, "SQSM_EDGE_CHUNK must be positive");
     edges.alloc(2 * E, st);
-    k_edges_expand<<<div_up(E, 256), 256, 0, st>>>(ebuf_i.p, ebuf_s.p, E, reinterpret_cast<longlong2*>(edges.p));
-    cx.launches += 2;
+    const int n_bounds = (int)(E / budget) + 2;
+    std::vector<int64_t> bounds(n_bounds);
+    {
+        DBuf<int64_t> d_bounds(n_bounds, st);
+        k_chunk_bounds<<<div_up(n_bounds, 128), 128, 0, st>>>(off.p, m, budget, n_bounds, d_bounds.p);
+        cx.launches++;
+        SQSM_CUDA(cudaMemcpyAsync(bounds.data(), d_bounds.p, sizeof(int64_t) * n_bounds, cudaMemcpyDeviceToHost, st));
+        SQSM_CUDA(cudaStreamSynchronize(st));
+    }
+    bounds[n_bounds - 1] = m;
+    std::vector<int64_t> cuts;                                   // strictly increasing node boundaries 0 .. m
+    cuts.push_back(0);
+    for (int k = 1; k < n_bounds; ++k) {
+        // off[bounds[k]] >= k * budget: stepping one node back keeps the chunk inside the budget (unless it is a single node)
+        int64_t c = std::min<int64_t>(bounds[k], m);
+        if (k < n_bounds - 1 && c - 1 > cuts.back()) c -= 1;
+        if (c > cuts.back()) cuts.push_back(c);
+    }
+    if (cuts.back() != m) cuts.push_back(m);
+    std::vector<int64_t> cut_off(cuts.size());
+    {
+        DBuf<int64_t> d_cuts((int64_t)cuts.size(), st), d_co((int64_t)cuts.size(), st);
+        SQSM_CUDA(cudaMemcpyAsync(d_cuts.p, cuts.data(), sizeof(int64_t) * cuts.size(), cudaMemcpyHostToDevice, st));
+        k_gather_i64<<<div_up((int64_t)cuts.size(), 128), 128, 0, st>>>(off.p, d_cuts.p, (int)cuts.size(), d_co.p);
+        cx.launches++;
+        SQSM_CUDA(cudaMemcpyAsync(cut_off.data(), d_co.p, sizeof(int64_t) * cuts.size(), cudaMemcpyDeviceToHost, st));
+        SQSM_CUDA(cudaStreamSynchronize(st));
+    }
+    for (size_t c = 0; c + 1 < cuts.size(); ++c) {
+        const int64_t i0 = cuts[c], i1 = cuts[c + 1], e0 = cut_off[c], ne = cut_off[c + 1] - cut_off[c];
+        if (ne == 0) continue;
+        SQSM_CHECK(ne < (1ll << 31), "radius graph: one node range holds more than 2^31 edges (lower SQSM_EDGE_CHUNK)");
+        DBuf<uint32_t> ebuf_i(ne, st), ebuf_j(ne, st), ebuf_s(ne, st);
+        k_radius_pairs<1><<<div_up(m, 256), 256, 0, st>>>(d_pts, order.p, cell_sorted.p, m, map.bnbr.p, cstart.p, r2, nullptr,
+                                                          off.p, (uint32_t)i0, (uint32_t)i1, ebuf_i.p, ebuf_j.p);
+        segmented_sort_u32(cx, ebuf_j.p, ebuf_s.p, ne, i1 - i0, off.p + i0, e0);
+        ebuf_j.release();
+        k_edges_expand<<<div_up(ne, 256), 256, 0, st>>>(ebuf_i.p, ebuf_s.p, ne, reinterpret_cast<longlong2*>(edges.p) + e0);
+        cx.launches += 2;
+    }
 }
 
 }  // namespace sqsm

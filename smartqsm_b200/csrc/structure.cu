@@ -62,7 +62,7 @@ __host__ __device__ __forceinline__ uint64_t cube_key(int cx, int cy, int cz) { 
 // ---------------------------------------------------------------------------------- tiling kernels
 
 __global__ void __launch_bounds__(256) k_cube_set(const float* __restrict__ P, int64_t n, float cs, BrickHash h,
-                                                  uint64_t* __restrict__ list, int32_t* __restrict__ counter,
+                                                  uint64_t* __restrict__ list, int list_cap, int32_t* __restrict__ counter,
                                                   int32_t* __restrict__ err) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -75,7 +75,10 @@ __global__ void __launch_bounds__(256) k_cube_set(const float* __restrict__ P, i
     bool ins;
     uint32_t slot = hash_insert(h, key, &ins);
     if (slot == 0xFFFFFFFFu) { atomicOr(err, 2); return; }
-    if (ins) list[atomicAdd(counter, 1)] = key;
+    if (ins) {
+        const int k = atomicAdd(counter, 1);
+        if (k < list_cap) list[k] = key; else atomicOr(err, 2);      // more distinct cubes than the list holds
+    }
 }
 
 // Enumerate the cube samples whose halo box contains point p (synthetic_tree.py:263-272).
@@ -162,12 +165,13 @@ void tile_points(Ctx& cx, const float* d_P, int64_t n, float cube_size, float bu
     hk.fill_ff();
     ctr.zero();
     BrickHash h{hk.p, hv.p, cap - 1};
-    k_cube_set<<<div_up(n, 256), 256, 0, st>>>(d_P, n, cube_size, h, list.p, ctr.p, ctr.p + 1);
+    k_cube_set<<<div_up(n, 256), 256, 0, st>>>(d_P, n, cube_size, h, list.p, (int)(cap / 2), ctr.p, ctr.p + 1);
     cx.launches++;
     int32_t hc[2];
     SQSM_CUDA(cudaMemcpyAsync(hc, ctr.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
     SQSM_CUDA(cudaStreamSynchronize(st));
-    SQSM_CHECK(hc[1] == 0, "cube index out of range (point coordinates / cube_size too large or NaN)");
+    SQSM_CHECK((hc[1] & 1) == 0, "cube index out of range (point coordinates / cube_size too large or NaN)");
+    SQSM_CHECK((hc[1] & 2) == 0, "unsupported number of cubes (more than 65534 occupied cubes)");
     int nc = hc[0];
     SQSM_CHECK(nc > 0 && nc < 65535 && nc <= (int)cap / 2, "unsupported number of cubes");
     std::vector<uint64_t> keys(nc);
@@ -221,7 +225,9 @@ void tile_points(Ctx& cx, const float* d_P, int64_t n, float cube_size, float bu
     SQSM_CUDA(cudaMemcpyAsync(&E32, off.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     SQSM_CUDA(cudaStreamSynchronize(st));      // also guarantees lut / samples were consumed from live host memory
     int64_t E = E32;
-    SQSM_CHECK(E > 0, "no cube sample contains any point");
+    // a point belongs to at most 8 cube samples; below 2^28 points the 32-bit scan cannot wrap, above it a negative or
+    // too small total gives the wrap away (every point has at least one membership: its own cube)
+    SQSM_CHECK(E >= n && E > 0, "cube-sample memberships overflow 2^31 entries (shard the cloud: ShardedTreeContraction)");
     out.n_entries = E;
     DBuf<uint32_t> es(E, st), ev(E, st);
     k_member_emit<<<div_up(n, 256), 256, 0, st>>>(d_P, n, tp, off.p, es.p, ev.p);
@@ -233,6 +239,7 @@ void tile_points(Ctx& cx, const float* d_P, int64_t n, float cube_size, float bu
     while ((1 << bits) < nc) ++bits;
     sort_pairs_u32(cx, es.p, out.ent_sample.p, ev.p, out.ent_val.p, E, 0, bits);
     DBuf<int64_t> d_start((int64_t)nc + 1, st);
+    d_start.zero();                            // a sample without entries (buffer_size = 0 corner cases) keeps a defined start
     k_boundaries<<<div_up(E, 256), 256, 0, st>>>(out.ent_sample.p, E, d_start.p);
     cx.launches++;
     out.start.assign((size_t)nc + 1, 0);

@@ -514,3 +514,62 @@ def test_multi_pass_iteration_is_bit_identical(random_state, monkeypatch):
         Pb, Db = multi.result()
         assert np.array_equal(Pa, Pb) and np.array_equal(Da, Db)
     assert b["gpu_launches"] > 2 * a["gpu_launches"], "the small limit must really have split the iteration into passes"
+
+
+# ---- round-2 regression tests (ADVICE.md findings of round 1)
+
+def test_skeletal_sample_cache_is_keyed_by_voxel(leafoff_state, small_tree):
+    """``voxel_size_for_downsampling`` is a pipeline parameter (thinning_based_skeletonization_pipeline.py:52,76): a second
+    call on the same state with another voxel must not return the cached sample of the first; the radius graph follows."""
+    eng = make_engine(leafoff_state)
+    eng.set_points(small_tree)
+    eng.contract_step()
+    P, D = eng.result()
+    for voxel in (0.01, 0.02, 0.01):
+        ids, sk, rad = eng.skeletal_sample(voxel)
+        ids_o, sk_o, rad_o = OC.skeletal_points_and_radii(P, D, voxel)
+        assert np.array_equal(ids, ids_o) and np.array_equal(sk, sk_o) and np.array_equal(rad, rad_o), voxel
+        assert np.array_equal(eng.radius_graph(0.055), OC.radius_edges(sk_o, 0.055)), voxel
+
+
+def test_fp16_range_guard_recovers(random_state):
+    """conv_mode 4/5: an activation >= 3e4 must raise, in BOTH FP16 modes, and must not poison the engine: the next
+    cloud on the same engine runs.  The first convolution sees absolute coordinates (F9), so a cloud 25 km away from the
+    origin drives the activations out of range while the same tree at the origin does not."""
+    from smartqsm_b200.synthetic import make_tree
+    state = dict(random_state)
+    state["input_conv.0.weight"] = state["input_conv.0.weight"] * 30.0
+    near = make_tree(20000, 8)
+    far = near + np.array([25000.0, 0.0, 0.0])
+    for mode in (4, 5):
+        eng = make_engine(state, conv_mode=mode)
+        eng.set_points(near)
+        assert eng.contract_step()["n_out"] > 0
+        eng.set_points(far)
+        with pytest.raises(RuntimeError, match="FP16 range"):
+            eng.contract_step()
+        eng.set_points(near)
+        assert eng.contract_step()["n_out"] > 0, "the range flag must be cleared after it tripped"
+
+
+def test_radius_graph_in_chunks(monkeypatch):
+    """The edge list is emitted in node-range chunks with 64-bit offsets (a 200 M-point scan has > 2^31 edges); tiny chunks
+    must give the identical list."""
+    from smartqsm_b200._lib import Engine
+    rng = np.random.default_rng(5)
+    pts = np.concatenate([rng.normal(0, 0.02, (2500, 3)), rng.uniform(-0.4, 0.4, (4000, 3))]).astype(np.float32)
+    eng = Engine()
+    e_ref = eng.radius_graph_points(pts, 0.055)
+    for budget in ("1000", "77777", "1"):
+        monkeypatch.setenv("SQSM_EDGE_CHUNK", budget)
+        assert np.array_equal(eng.radius_graph_points(pts, 0.055), e_ref), budget
+    monkeypatch.delenv("SQSM_EDGE_CHUNK")
+    assert np.array_equal(e_ref, OC.radius_edges(pts, 0.055))
+
+
+def test_inverse_conv_paths_agree(leafoff_state, small_tree, monkeypatch):
+    """The tensor-core inverse convolution (dense GEMM + scatter, upconv_tc.cu) and the FFMA kernel give the same state
+    within the split-mode tolerance; both are checked against the oracle by check_iteration."""
+    check_iteration(leafoff_state, small_tree)
+    monkeypatch.setenv("SQSM_UPCONV_FFMA", "1")
+    check_iteration(leafoff_state, small_tree)
