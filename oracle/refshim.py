@@ -244,6 +244,14 @@ def install() -> None:
     spp.modules = spm
     sys.modules.update({"spconv": sp, "spconv.pytorch": spp, "spconv.pytorch.utils": spu, "spconv.pytorch.modules": spm,
                         "open3d": _make_open3d()})
+    # imported at module level by files on the way to the skeletonisation pipelines but never touched on this path:
+    # cvxpy (utils/scipy_extra.py:6, used by an unrelated spline fit), distinctipy (utils/get_distinct_colors.py:1, GUI colours)
+    for name in ("cvxpy", "distinctipy", "distinctipy._colorsets_data"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            m.colors = []
+            sys.modules[name] = m
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     _installed = True
@@ -298,3 +306,38 @@ def reference_contraction(state: Dict[str, np.ndarray], **kwargs):
     finally:
         torch.load = real_load
     return obj
+
+
+# ------------------------------------------------------------------------------------ skeletonisation pipelines
+
+def reference_graph_stage(skeletal_points_f32: np.ndarray, radii: Optional[np.ndarray] = None, r: float = 0.055,
+                          edge_weight_function: str = "l1", topology_extractor: str = "spt"):
+    """The reference's OWN ``_construct_graph`` + ``_extract_skeleton``
+    (core/skeletonization_pipeline_base.py:75-238) on given skeletal points.  SciPy and networkx are the real
+    libraries; only ``open3d`` (touched in verbose branches) is a stub.  Returns the pipeline object: ``_edges``,
+    ``_graph``, ``_skeleton`` hold the results."""
+    install()
+    from core.skeletonization_pipeline_base import SkeletonizationPipelineBase
+    p = SkeletonizationPipelineBase(verbose=False)
+    p.set_params(edge_search_kwargs={"r": r}, edge_weight_function=edge_weight_function,
+                 topology_extractor=topology_extractor)
+    p._skeletal_points = np.ascontiguousarray(skeletal_points_f32, dtype=np.float32)
+    p._radii = radii
+    p._construct_graph()
+    edges = [list(e) for e in p._edges]
+    p._extract_skeleton()
+    p._merged_edges = np.array(edges, dtype=np.int64).reshape(-1, 2)
+    return p
+
+
+def reference_thinning_pipeline(registry_patch=None, **set_params_kwargs):
+    """The reference's ``ThinningBasedSkeletonizationPipeline`` (core/thinning_based_skeletonization_pipeline.py),
+    imported unmodified.  ``registry_patch(registry)`` may register another plug-in class before ``set_params``
+    looks the algorithm up (``:55-58``) - this is how the B200 plug-in is driven through the reference's own code."""
+    install()
+    import core.thinning_based_skeletonization_pipeline as T
+    if registry_patch is not None:
+        registry_patch(T.registry)
+    p = T.ThinningBasedSkeletonizationPipeline(verbose=False)
+    p.set_params(**set_params_kwargs)
+    return p
