@@ -133,6 +133,27 @@ int  sqsm_radius_graph(sqsm_handle h, double r, int64_t* n_edges, int64_t* h_edg
 int  sqsm_radius_graph_points(sqsm_handle h, const float* h_points_xyz, int64_t m, double r,
                               int64_t* n_edges, int64_t* h_edges_ij, int64_t capacity);
 
+/* ---- connectivity graph and skeleton extraction behind the path (SURVEY.md section 8 row a16 = f1) -----------------
+ * SkeletonizationPipelineBase._construct_graph (core/skeletonization_pipeline_base.py:75-174): edges of the Delaunay
+ * tetrahedra (`h_simplices` = scipy.spatial.Delaunay(points).simplices, int32 [t][4]: Qhull stays on the host, :77), its
+ * shortest-path tree from the lowest node of the largest component (networkx dijkstra_predecessor_and_distance,
+ * predecessors[0], :104-120) and its minimum spanning edges (Kruskal in networkx's edge order, :122-130), merged with the
+ * radius-neighbour edges (r <= 0: none) and optional preset edges into the sorted unique list of :158.
+ * `h_points_xyz` == NULL uses the skeletal points (and the cached radius graph) of the last sqsm_skeletal_sample(). */
+int  sqsm_graph_construct(sqsm_handle h, const float* h_points_xyz, int64_t m, const int32_t* h_simplices,
+                          int64_t n_simplices, double r, const int64_t* h_preset_edges_ij, int64_t n_preset,
+                          int64_t* n_edges);
+int  sqsm_graph_edges(sqsm_handle h, int64_t* h_edges_ij);              /* int64 [n_edges][2], i < j, lexicographic */
+/* {root of the Delaunay graph, unique Delaunay edges, SPT edges, MST edges, merged edges} */
+int  sqsm_graph_info(sqsm_handle h, int64_t* info5);
+/* Weighted graph (:160-174; weight_fn 0 = "l1", 1 = "l2") and _extract_skeleton with topology_extractor == "spt"
+ * (:190-215): root = lowest node of the largest component; h_pred[m] = predecessors[0] of every reached node (-1 for the
+ * root and for unreached nodes); h_order[n_reached - 1] = nodes in the order networkx inserted them into the predecessor
+ * dict (the reference adds the skeleton's edges in this order, :205-213); h_weight[m] = float32 length of the edge
+ * (pred, node).  Any output pointer may be NULL. */
+int  sqsm_graph_extract_skeleton(sqsm_handle h, int32_t weight_fn, int64_t* root, int64_t* n_reached, int64_t* h_pred,
+                                 int64_t* h_order, float* h_weight);
+
 /* ---- cloud preparation in front of the path ---------------------
  * Replaces entrypoints/smartqsm.py:882-913: bounding box -> global shift -> translate (:882-888),
  * Open3D voxel_down_sample, float64 voxel means (:889), Open3D remove_statistical_outlier

@@ -71,6 +71,7 @@ EXPORTS = [
     "sqsm_debug_batch_shapes", "sqsm_debug_level_tables", "sqsm_debug_canon_to_internal",
     "sqsm_debug_predictions", "sqsm_debug_features", "sqsm_profile_reset", "sqsm_profile_get",
     "sqsm_profile_enable", "sqsm_profile_families", "sqsm_timer_start", "sqsm_timer_stop", "sqsm_launch_count",
+    "sqsm_graph_construct", "sqsm_graph_edges", "sqsm_graph_info", "sqsm_graph_extract_skeleton",
     "sqsm_prepare_cloud_f64", "sqsm_prepared_size", "sqsm_get_prepared", "sqsm_set_points_prepared", "sqsm_debug_prepared", "sqsm_sizeof",
 ]
 
@@ -131,6 +132,10 @@ def load_library() -> C.CDLL:
         "sqsm_set_points_prepared": ([vp], C.c_int),
         "sqsm_debug_prepared": ([vp, vp, vp, vp], C.c_int),
         "sqsm_sizeof": ([i32], C.c_int),
+        "sqsm_graph_construct": ([vp, vp, i64, vp, i64, f64, vp, i64, P(i64)], C.c_int),
+        "sqsm_graph_edges": ([vp, vp], C.c_int),
+        "sqsm_graph_info": ([vp, vp], C.c_int),
+        "sqsm_graph_extract_skeleton": ([vp, i32, P(i64), P(i64), vp, vp, vp], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, name)
@@ -333,6 +338,44 @@ class Engine:
             self._check(self._lib.sqsm_radius_graph_points(self._h, _ptr(a), a.shape[0], r, C.byref(e), _ptr(out),
                                                            e.value), "radius_graph_points")
         return out
+
+    # ---- connectivity graph + skeleton extraction (row a16 / f1)
+    def graph_construct(self, simplices: np.ndarray, r: float = 0.055, points: Optional[np.ndarray] = None,
+                        preset_edges: Optional[np.ndarray] = None, fetch: bool = True):
+        """``_construct_graph`` (core/skeletonization_pipeline_base.py:75-174).  ``simplices`` = Delaunay tetrahedra of the
+        skeletal points (``scipy.spatial.Delaunay(points).simplices``); ``points=None`` uses the last skeletal sample."""
+        sx = np.ascontiguousarray(simplices, dtype=np.int32)
+        assert sx.ndim == 2 and sx.shape[1] == 4
+        pts = None if points is None else np.ascontiguousarray(points, dtype=np.float32)
+        pre = None if preset_edges is None else np.ascontiguousarray(preset_edges, dtype=np.int64).reshape(-1, 2)
+        e = C.c_int64()
+        self._check(self._lib.sqsm_graph_construct(self._h, _ptr(pts), 0 if pts is None else pts.shape[0], _ptr(sx), sx.shape[0],
+                                                   float(r) if r else 0.0, _ptr(pre), 0 if pre is None else pre.shape[0],
+                                                   C.byref(e)), "graph_construct")
+        if not fetch:
+            return e.value
+        out = np.empty((e.value, 2), np.int64)
+        if e.value:
+            self._check(self._lib.sqsm_graph_edges(self._h, _ptr(out)), "graph_edges")
+        return out
+
+    def graph_info(self) -> dict:
+        a = np.zeros(5, np.int64)
+        self._check(self._lib.sqsm_graph_info(self._h, _ptr(a)), "graph_info")
+        return dict(zip(("delaunay_root", "n_delaunay_edges", "n_spt_edges", "n_mst_edges", "n_edges"), (int(x) for x in a)))
+
+    def graph_extract_skeleton(self, n_nodes: int, edge_weight_function: str = "l1") -> dict:
+        """``_extract_skeleton`` with ``topology_extractor="spt"`` (:190-215) on the graph of ``graph_construct``."""
+        wf = {"l1": 0, "l2": 1}.get(edge_weight_function)
+        if wf is None:
+            raise NotImplementedError(f"edge weight function {edge_weight_function!r}: the device graph stage implements l1 and l2")
+        root, nr = C.c_int64(), C.c_int64()
+        pred = np.empty(n_nodes, np.int64)
+        order = np.empty(max(n_nodes - 1, 0), np.int64)
+        weight = np.empty(n_nodes, np.float32)
+        self._check(self._lib.sqsm_graph_extract_skeleton(self._h, wf, C.byref(root), C.byref(nr), _ptr(pred), _ptr(order),
+                                                          _ptr(weight)), "graph_extract_skeleton")
+        return {"root": root.value, "pred": pred, "order": order[:nr.value - 1], "weight": weight}
 
     # ---- inspection hooks
     def debug_capture(self, enable: bool = True) -> None:

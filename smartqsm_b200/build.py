@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsqsm_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["brickmap.cu", "structure.cu", "conv.cu", "conv_tc.cu", "upconv_tc.cu", "conv_tma.cu", "spatial.cu", "preprocess.cu", "engine.cu"]
+SOURCES = ["brickmap.cu", "structure.cu", "conv.cu", "conv_tc.cu", "conv_tma.cu", "spatial.cu", "graph.cu", "preprocess.cu", "engine.cu"]
 HEADERS = ["common.cuh", "brickmap.h", "engine.h", "tc_ptx.cuh", os.path.join("..", "..", "include", "sqsm_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

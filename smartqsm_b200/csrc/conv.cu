@@ -328,10 +328,6 @@ std::vector<float> make_tc_weight_image_f16(const float* w_kcico, int kv, int ci
 std::vector<float> make_tma_weight_image(const float* w_kcico, int kv, int ci, int co, int cs, int g);   // conv_tma.cu
 bool conv_tma_supported(int ci, int co, int kv, bool cat);
 int tma_group(int cs, int kv);
-std::vector<float> make_up_weight_image_f16(const float* w_kcico, int ci, int co);   // upconv_tc.cu
-bool upconv_tc(Ctx& cx, int ci, int co, const void* in_hi, const void* in_lo, const int32_t* child, const int32_t* parent,
-               const float* wimg, float* out, void* raw_hi, void* raw_lo, void* act_hi, void* act_lo, const float* act_alpha,
-               const float* act_beta, int* range_flag, int64_t n_coarse, int64_t n_fine);
 void act_split_rows(Ctx& cx, const float* in, const float* bn, int c, int bn_off, int bn_stride, int64_t n, void* out, int* range_flag);
 bool conv_tma(Ctx& cx, int ci, int co, int kv, bool cat, const void* splitA, const void* splitB, const int32_t* nbr, const float* wimg,
               const float* res, const float* sel_src, const uint8_t* sel_flag, float* out, int64_t n_out, int64_t n_in);
@@ -361,7 +357,7 @@ static void fold_bn(const std::map<std::string, std::vector<float>>& st, const s
 
 void net_upload(Ctx& cx, NetWeights& nw, const std::map<std::string, std::vector<float>>& st, bool down_flip) {
     std::vector<float> blob;
-    struct Pending { std::string name; size_t w_off, bn_off, img_off, img16_off; bool has_bn, has_img; int ci, co, kv; size_t tma_off = 0; bool has_tma = false; size_t up_off = 0; bool has_up = false; };
+    struct Pending { std::string name; size_t w_off, bn_off, img_off, img16_off; bool has_bn, has_img; int ci, co, kv; size_t tma_off = 0; bool has_tma = false; };
     std::vector<Pending> pend;
     auto add_conv = [&](const std::string& name, const std::string& wkey, const std::string& bnkey, int ci, int co, int kv,
                         int ci_pad, bool flip, bool cat = false) {
@@ -399,13 +395,6 @@ void net_upload(Ctx& cx, NetWeights& nw, const std::map<std::string, std::vector
             p.has_tma = true;
             blob.insert(blob.end(), img.begin(), img.end());
         }
-        if (name.size() > 3 && name.compare(name.size() - 3, 3, ".up") == 0) {      // inverse convolution as a dense GEMM (upconv_tc.cu)
-            std::vector<float> img = make_up_weight_image_f16(&blob[p.w_off], ci_pad, co);
-            while (blob.size() % 64) blob.push_back(0.0f);
-            p.up_off = blob.size();
-            p.has_up = true;
-            blob.insert(blob.end(), img.begin(), img.end());
-        }
         pend.push_back(p);
     };
     add_conv("input", "input_conv.0.weight", "", 3, kPlanes[0], 27, 4, false);
@@ -439,7 +428,6 @@ void net_upload(Ctx& cx, NetWeights& nw, const std::map<std::string, std::vector
         c.wimg = p.has_img ? nw.blob.p + p.img_off : nullptr;
         c.wimg16 = p.has_img ? nw.blob.p + p.img16_off : nullptr;
         c.wimg_tma = p.has_tma ? nw.blob.p + p.tma_off : nullptr;
-        c.wimg_up = p.has_up ? nw.blob.p + p.up_off : nullptr;
         nw.conv[p.name] = c;
     }
     // heads (App. A #48-51)
@@ -474,8 +462,8 @@ static void conv_dispatch(Ctx& cx, const ConvArgs& a) {
 // conv_tc.cu
 bool conv_tc(Ctx& cx, int ci, int co, int kv, bool cat, const float* inA, const float* inB, const float* inA_lo,
              const float* inB_lo, const int32_t* nbr, const float* wimg, const float* res, const float* sel_src,
-             const uint8_t* sel_flag, float* out, int64_t n_out, bool precise, bool f16, void* out_hi = nullptr,
-             void* out_lo = nullptr, const float* out_bn = nullptr, int* range_flag = nullptr);
+             const uint8_t* sel_flag, float* out, int64_t n_out, bool precise, bool f16, const TcFused* fused = nullptr,
+             int* range_flag = nullptr, const int32_t* up_parent = nullptr, const int32_t* up_koff = nullptr);
 void act_split(Ctx& cx, const float* in, const float* bn, int c, int bn_off, int bn_stride, int64_t n, float* hi, float* lo);
 void act_split_f16(Ctx& cx, const float* in, const float* bn, int c, int bn_off, int bn_stride, int64_t n, void* hi, void* lo,
                    int* range_flag);
@@ -500,9 +488,9 @@ static bool conv_ffma(Ctx& cx, const ConvW& w, bool cat, const ConvArgs& a) {
 }
 
 // One convolution of the network: tensor-core path for C_out >= 16 (inputs pre-activated once), FFMA otherwise.
-// Activation split handed from the convolution that produces a tensor to its ONE consumer: the producer's epilogue applies
-// the consumer's BatchNorm + ReLU and writes the FP16 hi / lo operands itself (conv_tc.cu), so the separate k_act_split_f16
-// pass and - when nothing else reads the tensor - its float32 round trip disappear.
+// Activation split handed from the convolution that produces a tensor to its consumers: the producer's epilogue applies
+// the consumer's BatchNorm + ReLU and writes the FP16 hi / lo operands itself (conv_tc.cu; bulk stores of whole tiles), so
+// the separate k_act_split_f16 pass and - when nothing else reads the tensor - its float32 round trip disappear.
 struct FusedSplit {
     DBuf<float> hi, lo;
     bool ready = false;
@@ -516,22 +504,34 @@ static bool layer_uses_tc(const NetWeights& nw, const ConvW& w, bool cat) {
     return nw.mode != 0 && w.wimg && (w.co >= nw.tc_min_co || (nw.mode >= 3 && cat && w.ci == 16 && w.co == 8 && w.kv == 27));
 }
 
+struct ConvOpts {
+    const float* res = nullptr;          // residual added to the output
+    const float* sel_src = nullptr;      // rows with sel_flag == 0 take this tensor instead ("batch did not descend")
+    const uint8_t* sel_flag = nullptr;
+    const FusedSplit* consume = nullptr;     // operands of the first (or only) source, already written by its producer
+    const FusedSplit* consumeB = nullptr;    // ... of the second source of a concat
+    FusedSplit* produce[2] = {nullptr, nullptr};     // operands to write for up to two consumers of the output
+    const float* p_alpha[2] = {nullptr, nullptr};    // their BatchNorm scale / shift (nullptr: raw values)
+    const float* p_beta[2] = {nullptr, nullptr};
+    bool need_fp32 = true;               // false: the float32 output has no reader (only with a fused split)
+    const int32_t* up_parent = nullptr;  // inverse convolution (kv = 8): rulebook from the down-sample tables
+    const int32_t* up_koff = nullptr;
+};
+
 static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, bool cat, const float* inA, const float* inB,
-                     const int32_t* nbr, float* out, int64_t n_out, int64_t n_in, const float* res = nullptr,
-                     const float* sel_src = nullptr, const uint8_t* sel_flag = nullptr, const FusedSplit* consume = nullptr,
-                     FusedSplit* produce = nullptr, const char* consumer = nullptr, bool need_fp32 = true,
-                     const FusedSplit* consumeB = nullptr) {
+                     const int32_t* nbr, float* out, int64_t n_out, int64_t n_in, const ConvOpts& op = ConvOpts()) {
     const ConvW& w = nw.conv.at(name);
-    if (produce) produce->ready = false;
+    for (int q = 0; q < 2; ++q) if (op.produce[q]) op.produce[q]->ready = false;
     if (n_out <= 0) return;
-    const bool use_tc = layer_uses_tc(nw, w, cat);
+    const bool up = op.up_parent != nullptr;
+    const bool use_tc = up ? (nw.mode == 3 && w.wimg16) : layer_uses_tc(nw, w, cat);
     // per-kernel scope: algorithmic bytes of SURVEY 8(d): features in + out, rulebook entries, residual re-read
     char fam[64];
-    snprintf(fam, sizeof(fam), "conv_%s_ci%d_co%d_k%d", use_tc ? "tc" : "ffma", w.ci, w.co, w.kv);
-    const double alg_bytes = 4.0 * ((double)n_in * w.ci + (double)n_out * w.co) + 4.0 * (nbr ? (double)w.kv * n_out : 0.0) +
-                             (res ? 4.0 * (double)n_out * w.co : 0.0);
+    snprintf(fam, sizeof(fam), "conv_%s%s_ci%d_co%d_k%d", use_tc ? "tc" : "ffma", up ? "_up" : "", w.ci, w.co, w.kv);
+    const double alg_bytes = 4.0 * ((double)n_in * w.ci + (double)n_out * w.co) +
+                             4.0 * (up ? 2.0 * n_out : (nbr ? (double)w.kv * n_out : 0.0)) + (op.res ? 4.0 * (double)n_out * w.co : 0.0);
     static const char* tma_only = getenv("SQSM_TMA_ONLY");        // debug: restrict the TMA kernel to layers whose name contains this
-    if (use_tc && nw.mode == 4 && w.wimg_tma && conv_tma_supported(w.ci, w.co, w.kv, cat) &&
+    if (use_tc && !up && nw.mode == 4 && w.wimg_tma && conv_tma_supported(w.ci, w.co, w.kv, cat) &&
         (!tma_only || name.find(tma_only) != std::string::npos)) {
         // activation + FP16 hi/lo split into "split rows", then the TMA-gather tensor-core kernel
         const int ca = cat ? w.ci / 2 : w.ci;
@@ -547,23 +547,22 @@ static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, boo
         }
         snprintf(fam, sizeof(fam), "conv_tma_ci%d_co%d_k%d", w.ci, w.co, w.kv);
         ProfScope ps(cx, fam, alg_bytes, 0.0);
-        if (conv_tma(cx, w.ci, w.co, w.kv, cat, sa.p, sb.p, nbr, w.wimg_tma, res, sel_src, sel_flag, out, n_out, n_in)) return;
+        if (conv_tma(cx, w.ci, w.co, w.kv, cat, sa.p, sb.p, nbr, w.wimg_tma, op.res, op.sel_src, op.sel_flag, out, n_out, n_in)) return;
         throw CudaError("conv_tma: unsupported shape for layer " + name);
     }
     if (use_tc) {
-        // activation + TF32 hi/lo split once per element, then the tensor-core implicit GEMM
+        // activation + hi/lo split once per element, then the tensor-core implicit GEMM
         const bool f16 = nw.mode == 3 || nw.mode == 4;
         const bool precise = nw.mode == 1 || f16;
         const int ca = cat ? w.ci / 2 : w.ci;
         // FP16 operands take half the space of TF32 ones: allocate in float units either way
         const int64_t elems = f16 ? (n_in * ca + 1) / 2 : n_in * ca;
         DBuf<float> a_hi, a_lo, b_hi, b_lo;
-        const float *pa_hi, *pa_lo, *pb_hi = nullptr, *pb_lo = nullptr;
-        // operands already written by the producer of the tensor (FusedSplit): first source / second source of a concat
-        const bool preA = consume && consume->ready && f16;
-        const bool preB = cat && consumeB && consumeB->ready && f16;
-        if (preA) { pa_hi = consume->hi.p; pa_lo = consume->lo.p; }
-        if (preB) { pb_hi = consumeB->hi.p; pb_lo = consumeB->lo.p; }
+        const float *pa_hi = nullptr, *pa_lo = nullptr, *pb_hi = nullptr, *pb_lo = nullptr;
+        const bool preA = op.consume && op.consume->ready && f16;
+        const bool preB = cat && op.consumeB && op.consumeB->ready && f16;
+        if (preA) { pa_hi = op.consume->hi.p; pa_lo = op.consume->lo.p; }
+        if (preB) { pb_hi = op.consumeB->hi.p; pb_lo = op.consumeB->lo.p; }
         if (!preA || (cat && !preB)) {
             ProfScope pa(cx, "act_split", (double)n_in * ca * ((preA ? 0 : 1) + (cat && !preB ? 1 : 0)) * (f16 ? 8.0 : 4.0 * (precise ? 3 : 2)), 0.0);
             if (!preA) {
@@ -583,30 +582,33 @@ static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, boo
                 pb_lo = b_lo.p;
             }
         }
-        // fused split for the consumer: only between two FP16 tensor-core layers, and the consumer must own a BatchNorm
-        void *o_hi = nullptr, *o_lo = nullptr;
-        const float* o_bn = nullptr;
-        if (produce && consumer && f16 && nw.mode == 3) {
-            const ConvW& wc = nw.conv.at(consumer);
-            if ((tc_f16_layer(nw, wc) || wc.wimg_up) && wc.bn && wc.ci == w.co) {
+        // fused splits for the consumers (FP16 mode only)
+        TcFused fused[2];
+        bool any_fused = false;
+        if (f16 && nw.mode == 3) {
+            for (int q = 0; q < 2; ++q) {
+                if (!op.produce[q]) continue;
                 const int64_t oe = (n_out * w.co + 1) / 2;
-                produce->hi.alloc(oe, cx.st);
-                produce->lo.alloc(oe, cx.st);
-                produce->ready = true;
-                o_hi = produce->hi.p; o_lo = produce->lo.p; o_bn = wc.bn;
+                op.produce[q]->hi.alloc(oe, cx.st);
+                op.produce[q]->lo.alloc(oe, cx.st);
+                op.produce[q]->ready = true;
+                fused[q].hi = op.produce[q]->hi.p; fused[q].lo = op.produce[q]->lo.p;
+                fused[q].alpha = op.p_alpha[q]; fused[q].beta = op.p_beta[q];
+                any_fused = true;
             }
         }
-        float* o_f32 = (o_hi && !need_fp32) ? nullptr : out;
+        float* o_f32 = (any_fused && !op.need_fp32) ? nullptr : out;
         ProfScope ps(cx, fam, alg_bytes, 0.0);
-        if (conv_tc(cx, w.ci, w.co, w.kv, cat, pa_hi, pb_hi, pa_lo, pb_lo, nbr, f16 ? w.wimg16 : w.wimg, res, sel_src, sel_flag,
-                    o_f32, n_out, precise, f16, o_hi, o_lo, o_bn, nw.range_flag))
+        if (conv_tc(cx, w.ci, w.co, w.kv, cat, pa_hi, pb_hi, pa_lo, pb_lo, nbr, f16 ? w.wimg16 : w.wimg, op.res, op.sel_src,
+                    op.sel_flag, o_f32, n_out, precise, f16, any_fused ? fused : nullptr, nw.range_flag, op.up_parent, op.up_koff))
             return;
-        if (produce) produce->ready = false;
+        for (int q = 0; q < 2; ++q) if (op.produce[q]) op.produce[q]->ready = false;
+        if (up) throw CudaError("no tensor-core kernel for inverse convolution " + name);
     }
     ProfScope ps(cx, fam, alg_bytes, 0.0);
     ConvArgs ar;
-    ar.inA = inA; ar.inB = inB; ar.nbr = nbr; ar.w = w.w; ar.bn = w.bn; ar.res = res; ar.sel_src = sel_src;
-    ar.sel_flag = sel_flag; ar.out = out; ar.n_out = (int)n_out; ar.kc = 0;
+    ar.inA = inA; ar.inB = inB; ar.nbr = nbr; ar.w = w.w; ar.bn = w.bn; ar.res = op.res; ar.sel_src = op.sel_src;
+    ar.sel_flag = op.sel_flag; ar.out = out; ar.n_out = (int)n_out; ar.kc = 0;
     if (!conv_ffma(cx, w, cat, ar)) throw CudaError("no convolution kernel for layer " + name);
 }
 
@@ -627,8 +629,15 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
     cudaStream_t st = cx.st;
     SQSM_CHECK(nw.ready, "weights not finalised");
     DBuf<float> enc[kLevels], tmp[kLevels];
-    const bool up_on_tc = nw.mode == 3 && getenv("SQSM_UPCONV_FFMA") == nullptr;   // inverse convolutions as dense GEMMs (upconv_tc.cu)
+    // FP16 split mode: producers write their consumers' operands (FusedSplit); inverse convolutions on the tensor cores
+    const bool fuse = nw.mode == 3 && getenv("SQSM_NO_FUSED_SPLIT") == nullptr;
+    const bool up_on_tc = nw.mode == 3 && getenv("SQSM_UPCONV_FFMA") == nullptr;
+    FusedSplit sp_in;                        // operands of the level's first convolution, written by the down convolution
+    FusedSplit sp_down[kLevels];             // enc[l] as operands of the down convolution of level l
+    FusedSplit sp_skip[kLevels];             // enc[l] as operands (first half of the concat) of tail.a of level l
     FusedSplit sp_cur;                       // operands of the next inverse convolution, written by the producer of `cur`
+    auto bn_a = [](const ConvW& w, int off) { return w.bn ? w.bn + off : nullptr; };
+    auto bn_b = [](const ConvW& w, int off) { return w.bn ? w.bn + w.ci + off : nullptr; };
     // ---- encoder (smart_tree_xx.py:65-66, sparse_module.py:101-112)
     const int64_t n0 = lv[0].n;
     DBuf<float> cur_in(n0 * 8, st);
@@ -641,29 +650,47 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
         const int64_t n = lv[l].n;
         const int c = kPlanes[l];
         const std::string L = "L" + std::to_string(l);
+        const bool deepest = l == n_levels - 1;
         enc[l].alloc(n * c, st);
         tmp[l].alloc(n * c, st);
         {   // ResidualBlock with identity i_branch (sparse_module.py:32-39): out = convB(bnrelu(convA(bnrelu(x)))) + x
             ProfScope pt(cx, lvl_family(l), 2.0 * (4.0 * n * c * 2 + 4.0 * 27 * n) + 4.0 * n * c,
                          2.0 * 2.0 * (double)lv[l].pairs * c * c);
             FusedSplit sp_mid;                                  // bnrelu(convA(.)) as convB's operands, written by convA
-            const std::string nb = L + ".blk.b";
-            conv_any(cx, nw, L + ".blk.a", false, cur_in.p, nullptr, lv[l].nbr.p, tmp[l].p, n, n, nullptr, nullptr, nullptr, nullptr,
-                     &sp_mid, nb.c_str(), /*need_fp32=*/false);
-            // the deepest level feeds the inverse convolution only: its epilogue writes that layer's operands
-            const bool deepest = (l == n_levels - 1) && l > 0 && up_on_tc;
-            const std::string upn = "L" + std::to_string(l - 1) + ".up";
-            conv_any(cx, nw, nb, false, tmp[l].p, nullptr, lv[l].nbr.p, enc[l].p, n, n, cur_in.p, nullptr, nullptr, &sp_mid,
-                     deepest ? &sp_cur : nullptr, deepest ? upn.c_str() : nullptr, /*need_fp32=*/keep || !deepest);
+            const ConvW& wb = nw.conv.at(L + ".blk.b");
+            ConvOpts oa;
+            oa.consume = &sp_in;
+            if (fuse && tc_f16_layer(nw, wb)) { oa.produce[0] = &sp_mid; oa.p_alpha[0] = bn_a(wb, 0); oa.p_beta[0] = bn_b(wb, 0); oa.need_fp32 = false; }
+            conv_any(cx, nw, L + ".blk.a", false, cur_in.p, nullptr, lv[l].nbr.p, tmp[l].p, n, n, oa);
+            ConvOpts ob;
+            ob.res = cur_in.p;
+            ob.consume = &sp_mid;
+            if (fuse && deepest && l > 0 && up_on_tc) {
+                // the deepest level feeds the inverse convolution only: its epilogue writes that layer's operands
+                const ConvW& wu = nw.conv.at("L" + std::to_string(l - 1) + ".up");
+                ob.produce[0] = &sp_cur; ob.p_alpha[0] = bn_a(wu, 0); ob.p_beta[0] = bn_b(wu, 0);
+                ob.need_fp32 = keep;
+            } else if (fuse && !deepest) {
+                // the skip tensor: operands of the down convolution and of the tail block's first convolution
+                const ConvW& wd = nw.conv.at(L + ".down");
+                const ConvW& wa = nw.conv.at(L + ".tail.a");
+                if (layer_uses_tc(nw, wd, false)) { ob.produce[0] = &sp_down[l]; ob.p_alpha[0] = bn_a(wd, 0); ob.p_beta[0] = bn_b(wd, 0); }
+                if (layer_uses_tc(nw, wa, true)) { ob.produce[1] = &sp_skip[l]; ob.p_alpha[1] = bn_a(wa, 0); ob.p_beta[1] = bn_b(wa, 0); }
+            }
+            conv_any(cx, nw, L + ".blk.b", false, tmp[l].p, nullptr, lv[l].nbr.p, enc[l].p, n, n, ob);
         }
+        sp_in = FusedSplit();
         if (keep) keep_copy(cx, fb, "enc" + std::to_string(l), enc[l].p, n, c, l);
-        if (l + 1 < n_levels) {
+        if (!deepest) {
             const int64_t nn = lv[l + 1].n;
             DBuf<float> nxt(nn * kPlanes[l + 1], st);
             ProfScope pt(cx, "down_up", 4.0 * (n * c + nn * kPlanes[l + 1]) + 4.0 * n, 2.0 * (double)n * c * kPlanes[l + 1]);
-            // (no fused split here: the k = 8 down convolution is epilogue bound, the extra stores cost more than the
-            // separate split pass - measured 9.8 -> 21 ms per C3 step for 16 -> 32)
-            conv_any(cx, nw, L + ".down", false, enc[l].p, nullptr, lv[l].child.p, nxt.p, nn, n);
+            const ConvW& wn = nw.conv.at("L" + std::to_string(l + 1) + ".blk.a");
+            ConvOpts od;
+            od.consume = &sp_down[l];
+            if (fuse && tc_f16_layer(nw, wn)) { od.produce[0] = &sp_in; od.p_alpha[0] = bn_a(wn, 0); od.p_beta[0] = bn_b(wn, 0); }
+            conv_any(cx, nw, L + ".down", false, enc[l].p, nullptr, lv[l].child.p, nxt.p, nn, n, od);
+            sp_down[l] = FusedSplit();
             cur_in = std::move(nxt);
         }
     }
@@ -676,29 +703,24 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
         const ConvW& wu = nw.conv.at(L + ".up");
         const ConvW& wi = nw.conv.at(L + ".tail.i");
         const ConvW& wa = nw.conv.at(L + ".tail.a");
+        const ConvW& wb = nw.conv.at(L + ".tail.b");
         DBuf<float> up, res(n * c, st), out(n * c, st);
         FusedSplit up_raw, up_act;           // the decoder half of the concat as operands of tail.i (raw) and tail.a (BN + ReLU)
         {
             ProfScope pt(cx, "down_up", 4.0 * (nc * cn + n * c) + 4.0 * n, 2.0 * (double)n * c * cn);
-            if (up_on_tc && wu.wimg_up) {
-                if (!sp_cur.ready) {                          // producer could not fuse the split (FFMA layer): one pass
-                    const int64_t e = (nc * cn + 1) / 2;
-                    sp_cur.hi.alloc(e, st);
-                    sp_cur.lo.alloc(e, st);
-                    ProfScope pa(cx, "act_split", (double)nc * cn * 8.0, 0.0);
-                    act_split_f16(cx, cur.p, wu.bn, cn, 0, cn, nc, sp_cur.hi.p, sp_cur.lo.p, nw.range_flag);
-                }
-                const bool i_tc = layer_uses_tc(nw, wi, true) && nw.mode == 3, a_tc = layer_uses_tc(nw, wa, true) && nw.mode == 3;
-                const int64_t e = (n * c + 1) / 2;
-                if (i_tc) { up_raw.hi.alloc(e, st); up_raw.lo.alloc(e, st); up_raw.ready = true; }
-                if (a_tc) { up_act.hi.alloc(e, st); up_act.lo.alloc(e, st); up_act.ready = true; }
-                if (!i_tc || !a_tc) up.alloc(n * c, st);      // a float32 consumer remains
-                char fam[64];
-                snprintf(fam, sizeof(fam), "conv_tc_up_ci%d_co%d", cn, c);
-                ProfScope ps(cx, fam, 4.0 * ((double)nc * cn + (double)n * c) + 4.0 * 8 * (double)nc, 0.0);
-                if (!upconv_tc(cx, cn, c, sp_cur.hi.p, sp_cur.lo.p, lv[l].child.p, lv[l].parent.p, wu.wimg_up, up.p, up_raw.hi.p,
-                               up_raw.lo.p, up_act.hi.p, up_act.lo.p, wa.bn + c, wa.bn + 2 * c + c, nw.range_flag, nc, n))
-                    throw CudaError("upconv_tc: unsupported shape");
+            if (up_on_tc && wu.wimg16) {
+                // SparseInverseConv3d as a gather convolution with 8 offsets: the rulebook entry (k, fine row) exists for
+                // k == koff[row] only (App. A); rows without a parent gather nothing and come out as 0 / relu(beta)
+                const bool i_tc = layer_uses_tc(nw, wi, true), a_tc = layer_uses_tc(nw, wa, true);
+                ConvOpts ou;
+                ou.consume = &sp_cur;
+                ou.up_parent = lv[l].parent.p;
+                ou.up_koff = lv[l].koff.p;
+                if (fuse && i_tc) { ou.produce[0] = &up_raw; }
+                if (fuse && a_tc) { ou.produce[1] = &up_act; ou.p_alpha[1] = bn_a(wa, c); ou.p_beta[1] = bn_b(wa, c); }
+                ou.need_fp32 = !(fuse && i_tc && a_tc);
+                if (ou.need_fp32) up.alloc(n * c, st);
+                conv_any(cx, nw, L + ".up", false, cur.p, nullptr, nullptr, up.p, n, nc, ou);
             } else {
                 up.alloc(n * c, st);
                 if (l == 0) launch_upconv<16, 8>(cx, wu, cur.p, lv[l].parent.p, lv[l].koff.p, up.p, n);
@@ -710,17 +732,28 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
         {   // blocks_tail on cat(enc, up); rows of batches that did not descend keep `enc`
             ProfScope pt(cx, lvl_family(l), 4.0 * n * (2 * c + c) * 2 + 4.0 * n * (c + c) + 2.0 * 4.0 * 27 * n + 4.0 * n * c,
                          2.0 * (double)lv[l].pairs * (2 * c * c + c * c) + 2.0 * (double)n * 2 * c * c);
-            conv_any(cx, nw, L + ".tail.i", true, enc[l].p, up.p, nullptr, res.p, n, n, nullptr, nullptr, nullptr, nullptr, nullptr,
-                     nullptr, true, &up_raw);
+            ConvOpts oi;
+            oi.consumeB = &up_raw;
+            conv_any(cx, nw, L + ".tail.i", true, enc[l].p, up.p, nullptr, res.p, n, n, oi);
+            up_raw = FusedSplit();
             FusedSplit sp_mid;
-            const std::string nb = L + ".tail.b";
-            conv_any(cx, nw, L + ".tail.a", true, enc[l].p, up.p, lv[l].nbr.p, tmp[l].p, n, n, nullptr, nullptr, nullptr, nullptr,
-                     &sp_mid, nb.c_str(), /*need_fp32=*/false, &up_act);
+            ConvOpts oa;
+            oa.consume = &sp_skip[l];
+            oa.consumeB = &up_act;
+            if (fuse && tc_f16_layer(nw, wb)) { oa.produce[0] = &sp_mid; oa.p_alpha[0] = bn_a(wb, 0); oa.p_beta[0] = bn_b(wb, 0); oa.need_fp32 = false; }
+            conv_any(cx, nw, L + ".tail.a", true, enc[l].p, up.p, lv[l].nbr.p, tmp[l].p, n, n, oa);
+            sp_skip[l] = FusedSplit();
+            up_act = FusedSplit();
             // the level's output feeds the next inverse convolution only (levels >= 1): fused operands, no float32 copy
-            const bool feeds_up = l > 0 && up_on_tc;
-            const std::string upn = "L" + std::to_string(l - 1) + ".up";
-            conv_any(cx, nw, nb, false, tmp[l].p, nullptr, lv[l].nbr.p, out.p, n, n, res.p, enc[l].p, lv[l].row_desc.p, &sp_mid,
-                     feeds_up ? &sp_cur : nullptr, feeds_up ? upn.c_str() : nullptr, /*need_fp32=*/keep || !feeds_up);
+            ConvOpts ob;
+            ob.res = res.p; ob.sel_src = enc[l].p; ob.sel_flag = lv[l].row_desc.p;
+            ob.consume = &sp_mid;
+            if (fuse && l > 0 && up_on_tc) {
+                const ConvW& wn = nw.conv.at("L" + std::to_string(l - 1) + ".up");
+                ob.produce[0] = &sp_cur; ob.p_alpha[0] = bn_a(wn, 0); ob.p_beta[0] = bn_b(wn, 0);
+                ob.need_fp32 = keep;
+            }
+            conv_any(cx, nw, L + ".tail.b", false, tmp[l].p, nullptr, lv[l].nbr.p, out.p, n, n, ob);
         }
         if (keep) keep_copy(cx, fb, "dec" + std::to_string(l), out.p, n, c, l);
         cur = std::move(out);

@@ -33,21 +33,27 @@ namespace sqsm {
 
 // ------------------------------------------------------------------------------------------ kernel
 
+struct TcSplitOut {            // fused activation split for one consumer of this output: hi/lo = split(act(out))
+    __half* hi;                // [n_out][CO] or nullptr
+    __half* lo;
+    const float* alpha;        // [CO] scale / shift of the consumer's BatchNorm (+ ReLU); nullptr = raw values
+    const float* beta;
+};
+
 struct TcArgs {
     const float* inA;         // [n_in][CI] TF32 hi part of the activated input (or first CI/2 channels when CAT)
     const float* inB;         // hi part of the second CI/2 channels when CAT
     const float* inA_lo;      // matching lo parts (PRECISE)
     const float* inB_lo;
     const int32_t* nbr;       // [KV][n_out] or nullptr (identity, KV == 1)
+    const int32_t* up_parent; // UP (inverse convolution): coarse row of every output row or -1, and its kernel offset;
+    const int32_t* up_koff;   //   the rulebook entry (k, row) is parent[row] when koff[row] == k, absent otherwise
     const float* wimg;        // per chunk: hi tile [NP][32] then lo tile [NP][32], SWIZZLE_128B images
     const float* res;         // [n_out][CO] or nullptr
     const float* sel_src;     // [n_out][CO] or nullptr
     const uint8_t* sel_flag;
-    float* out;               // [n_out][CO], or nullptr when only the fused split below is wanted
-    // fused activation split for the one consumer of this output (F16 kernels): hi/lo = split(relu(out * alpha + beta))
-    __half* out_hi;           // [n_out][CO] or nullptr
-    __half* out_lo;
-    const float* out_bn;      // alpha[CO] then beta[CO] of the consumer's BatchNorm
+    float* out;               // [n_out][CO], or nullptr when only the fused splits below are wanted
+    TcSplitOut sp[2];         // F16 kernels: operands of up to two consumers, written by the epilogue
     int* range_flag;
     int n_out;
     int n_tiles;
@@ -62,8 +68,14 @@ constexpr int kTcEpilogue = 128;      // next 4 warps: TMEM -> registers -> glob
 __host__ __device__ constexpr int tc_threads(int gr) { return gr * kTcProducers + kTcEpilogue + 32; }   // last warp: MMA issuer
 constexpr uint32_t kTmemCols = 256;   // two accumulator stages of up to 128 columns ([hi*hi + lo*hi | hi*lo] when PRECISE)
 
-__host__ __device__ constexpr int tc_stages(int np) {
-    int fit = (227 * 1024 - 2048) / (2 * 128 * 128 + 2 * np * 128);
+// Bulk epilogue (FP16 kernels with C_out <= 32): the 128 output rows of a tile are contiguous in global memory, so the
+// epilogue stages the float32 tile and the fused operand tiles in shared memory and one thread stores each with a single
+// cp.async.bulk (TMA); the residual tile arrives the same way.  A thread-per-row epilogue costs one LSU sector operation
+// per 16 bytes (32 rows x 16 B per instruction) and competes with the cp.async gather for the same L1TEX path.
+__host__ __device__ constexpr bool tc_bulk(int co, bool f16, bool precise) { return f16 && precise && co <= 32; }
+__host__ __device__ constexpr int tc_staging_bytes(int co, bool bulk) { return bulk ? 128 * co * 16 : 0; }   // out, res, 2 x (hi, lo)
+__host__ __device__ constexpr int tc_stages(int np, int staging = 0) {
+    int fit = (227 * 1024 - 2048 - staging) / (2 * 128 * 128 + 2 * np * 128);
     return fit > kTcMaxStages ? kTcMaxStages : fit;
 }
 
@@ -71,7 +83,7 @@ __host__ __device__ constexpr int tc_stages(int np) {
 // F16 = true : FP16 operands (2 B), 64 K elements per chunk row, kind::f16 - half the bytes to gather, half the
 //              LDGSTS instructions and half the shared-memory operand traffic per K element; the 2-term split
 //              hi = fp16(x), lo = fp16(x - hi) carries the same 22 mantissa bits as the TF32 split
-template <int CI, int CO, int KV, bool CAT, bool PRECISE, bool F16, int GR>
+template <int CI, int CO, int KV, bool CAT, bool PRECISE, bool F16, int GR, bool UP>
 __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_constant__ TcArgs a) {
     constexpr int kTcGroups = GR, kTcProdWarps = GR * 4;
     constexpr int KT = KV * CI;                       // GEMM K
@@ -83,7 +95,8 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
     constexpr int A_BYTES = 128 * 128;
     constexpr int B_BYTES = NP * 128;
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    constexpr int kTcStages = tc_stages(NP);
+    constexpr bool BULK = tc_bulk(CO, F16, PRECISE);
+    constexpr int kTcStages = tc_stages(NP, tc_staging_bytes(CO, BULK));
     constexpr uint32_t FMT = F16 ? 0u : 2u;           // a/b format: F16 = 0, TF32 = 2 (UMMA::F16F32Format)
     constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     // PRECISE: the hi and lo weight tiles are adjacent in shared memory ([NP rows][128 B] each), so ONE instruction with
@@ -95,7 +108,7 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B needs 1024 B alignment
-    __shared__ __align__(8) uint64_t bars[2 * kTcMaxStages + 4];
+    __shared__ __align__(8) uint64_t bars[2 * kTcMaxStages + 5];
     __shared__ uint32_t tmem_slot;
 
     const int t = threadIdx.x;
@@ -106,6 +119,7 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
     if (t == 0) {
         for (int s = 0; s < kTcStages; ++s) { mbar_init(full0 + 8 * s, kTcProducers); mbar_init(empty0 + 8 * s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, kTcEpilogue); }
+        mbar_init(smem_u32(&bars[2 * kTcMaxStages + 4]), 1);      // residual tile landed (bulk epilogue)
         fence_barrier_init();
     }
     if (warp == kTcProdWarps + 4) tmem_alloc(smem_u32(&tmem_slot), kTmemCols);
@@ -141,7 +155,12 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
             for (int q = 0; q < KPC; ++q) {
                 const int k = (j * CE) / CI + q;
                 int n = -1;
-                if (row < a.n_out && k < KV) n = a.nbr ? __ldg(a.nbr + (size_t)k * a.n_out + row) : row;
+                if (UP) {
+                    if (row < a.n_out && k < KV) {
+                        const int pr = __ldg(a.up_parent + row);
+                        if (pr >= 0 && __ldg(a.up_koff + row) == k) n = pr;
+                    }
+                } else if (row < a.n_out && k < KV) n = a.nbr ? __ldg(a.nbr + (size_t)k * a.n_out + row) : row;
                 nb[q] = n;
             }
         };
@@ -201,13 +220,30 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
     } else if (warp < kTcProdWarps + 4) {
         // ===================== epilogue: TMEM -> registers -> residual / select -> global =====================
         const int te = t - kTcGroups * kTcProducers;      // tile row, also the TMEM lane
-        uint32_t tile_it = 0;
+        // staging tiles of the bulk epilogue, behind the stage ring (row-major like global memory: one bulk copy per tile)
+        float* const out_s = reinterpret_cast<float*>(smem + (size_t)kTcStages * STAGE_BYTES);
+        float* const res_s = out_s + 128 * CO;
+        __half* const sp_s = reinterpret_cast<__half*>(res_s + 128 * CO);      // [2 splits][hi, lo][128][CO]
+        const uint32_t res_bar = smem_u32(&bars[2 * kTcMaxStages + 4]);
+        uint32_t tile_it = 0, res_it = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tile_it) {
             const uint32_t as = tile_it & 1u, aph = (tile_it >> 1) & 1u;
             const int row = tile * 128 + te;
             const bool live = row < a.n_out;
+            const uint32_t rows_valid = (uint32_t)min(128, a.n_out - tile * 128);
+            if (BULK && a.res && te == 0) {
+                // every epilogue thread passed the barrier in front of the previous tile's stores, i.e. finished reading
+                // res_s: the residual tile of this tile can land while its MMAs are still running
+                mbar_arrive_expect_tx(res_bar, rows_valid * CO * 4u);
+                bulk_g2s(smem_u32(res_s), a.res + (size_t)tile * 128 * CO, rows_valid * CO * 4u, res_bar);
+            }
             mbar_wait(tfull0 + 8 * as, aph);
             tc_fence_after();
+            if (BULK) {
+                if (te == 0) bulk_wait_read();              // the previous tile's bulk stores have read the staging tiles
+                named_barrier(1, kTcEpilogue);
+                if (a.res) { mbar_wait(res_bar, res_it & 1u); ++res_it; }
+            }
             const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + as * ACC;
             const size_t o = (size_t)row * CO;
             const bool take_src = live && a.sel_flag && a.sel_flag[row] == 0;
@@ -225,54 +261,78 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
                     tc_fence_before();
                     mbar_arrive(tempty0 + 8 * as);          // all columns read: this accumulator stage may be overwritten
                 }
-                if (live && c0 < CO) {
+                if ((BULK || live) && c0 < CO) {
                     #pragma unroll
                     for (int c = 0; c < 16 && c0 + c < CO; c += 8) {      // CO may be 8 (NP padded to 16)
+                        const int ch = c0 + c;
                         float r[8];
                         #pragma unroll
                         for (int i = 0; i < 8; ++i) r[i] = v[c + i];
                         if (a.res) {
-                            const float4 e0 = *reinterpret_cast<const float4*>(a.res + o + c0 + c);
-                            const float4 e1 = *reinterpret_cast<const float4*>(a.res + o + c0 + c + 4);
+                            const float* rp = BULK ? res_s + te * CO + ch : a.res + o + ch;
+                            const float4 e0 = *reinterpret_cast<const float4*>(rp);
+                            const float4 e1 = *reinterpret_cast<const float4*>(rp + 4);
                             r[0] += e0.x; r[1] += e0.y; r[2] += e0.z; r[3] += e0.w;
                             r[4] += e1.x; r[5] += e1.y; r[6] += e1.z; r[7] += e1.w;
                         }
                         if (take_src) {
-                            const float4 e0 = *reinterpret_cast<const float4*>(a.sel_src + o + c0 + c);
-                            const float4 e1 = *reinterpret_cast<const float4*>(a.sel_src + o + c0 + c + 4);
+                            const float4 e0 = *reinterpret_cast<const float4*>(a.sel_src + o + ch);
+                            const float4 e1 = *reinterpret_cast<const float4*>(a.sel_src + o + ch + 4);
                             r[0] = e0.x; r[1] = e0.y; r[2] = e0.z; r[3] = e0.w;
                             r[4] = e1.x; r[5] = e1.y; r[6] = e1.z; r[7] = e1.w;
                         }
                         if (a.out) {
-                            *reinterpret_cast<float4*>(a.out + o + c0 + c) = make_float4(r[0], r[1], r[2], r[3]);
-                            *reinterpret_cast<float4*>(a.out + o + c0 + c + 4) = make_float4(r[4], r[5], r[6], r[7]);
+                            float* op = BULK ? out_s + te * CO + ch : a.out + o + ch;
+                            *reinterpret_cast<float4*>(op) = make_float4(r[0], r[1], r[2], r[3]);
+                            *reinterpret_cast<float4*>(op + 4) = make_float4(r[4], r[5], r[6], r[7]);
                         }
-                        if (F16 && a.out_hi) {               // the consumer's BN + ReLU + FP16 hi/lo split, fused: 16-byte stores
-                            const int ch = c0 + c;
-                            float x[8];
-                            float mx = 0.f;
+                        if (F16) {
                             #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                x[i] = fmaxf(fmaf(r[i], a.out_bn[ch + i], a.out_bn[CO + ch + i]), 0.f);
-                                mx = fmaxf(mx, x[i]);
+                            for (int q = 0; q < 2; ++q) {    // the consumers' BN + ReLU + FP16 hi/lo split, fused: 16-byte stores
+                                if (!a.sp[q].hi) continue;
+                                float x[8];
+                                float mx = 0.f;
+                                #pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    x[i] = a.sp[q].alpha ? fmaxf(fmaf(r[i], a.sp[q].alpha[ch + i], a.sp[q].beta[ch + i]), 0.f) : r[i];
+                                    mx = fmaxf(mx, fabsf(x[i]));
+                                }
+                                if (live && !(mx < 3.0e4f)) *a.range_flag = 1;
+                                uint32_t hw[4], lw[4];
+                                #pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+                                    const float2 f = __half22float2(h);
+                                    const __half2 l = __floats2half2_rn(x[2 * i] - f.x, x[2 * i + 1] - f.y);
+                                    hw[i] = *reinterpret_cast<const uint32_t*>(&h);
+                                    lw[i] = *reinterpret_cast<const uint32_t*>(&l);
+                                }
+                                __half* hp = BULK ? sp_s + (2 * q) * 128 * CO + te * CO + ch : a.sp[q].hi + o + ch;
+                                __half* lp = BULK ? sp_s + (2 * q + 1) * 128 * CO + te * CO + ch : a.sp[q].lo + o + ch;
+                                *reinterpret_cast<uint4*>(hp) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                                *reinterpret_cast<uint4*>(lp) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                             }
-                            if (!(mx < 3.0e4f)) *a.range_flag = 1;
-                            uint32_t hw[4], lw[4];
-                            #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
-                                const float2 f = __half22float2(h);
-                                const __half2 l = __floats2half2_rn(x[2 * i] - f.x, x[2 * i + 1] - f.y);
-                                hw[i] = *reinterpret_cast<const uint32_t*>(&h);
-                                lw[i] = *reinterpret_cast<const uint32_t*>(&l);
-                            }
-                            *reinterpret_cast<uint4*>(a.out_hi + o + ch) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                            *reinterpret_cast<uint4*>(a.out_lo + o + ch) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                         }
                     }
                 }
             }
+            if (BULK) {
+                fence_proxy_async();                        // staging tiles were written through the generic proxy
+                named_barrier(2, kTcEpilogue);
+                if (te == 0) {
+                    const size_t t0 = (size_t)tile * 128 * CO;
+                    if (a.out) bulk_s2g(a.out + t0, smem_u32(out_s), rows_valid * CO * 4u);
+                    #pragma unroll
+                    for (int q = 0; q < 2; ++q)
+                        if (a.sp[q].hi) {
+                            bulk_s2g(a.sp[q].hi + t0, smem_u32(sp_s + (2 * q) * 128 * CO), rows_valid * CO * 2u);
+                            bulk_s2g(a.sp[q].lo + t0, smem_u32(sp_s + (2 * q + 1) * 128 * CO), rows_valid * CO * 2u);
+                        }
+                    bulk_commit();
+                }
+            }
         }
+        if (BULK && te == 0) bulk_wait_all();               // stores complete before the shared memory goes away
     } else if ((t & 31) == 0) {
         // ===================== MMA issuer: one thread =====================
         uint32_t it = 0, tile_it = 0;
@@ -429,51 +489,69 @@ std::vector<float> make_tc_weight_image_f16(const float* w_kcico, int kv, int ci
     return out;
 }
 
-template <int CI, int CO, int KV, bool CAT>
+template <int CI, int CO, int KV, bool CAT, bool UP>
 static void launch_tc(Ctx& cx, const TcArgs& a0, bool precise, bool f16) {
     constexpr int GR = ((CAT ? CI / 2 : CI) == 16 && KV == 27) ? 3 : 2;      // FP16 kernels only (the default path)
     TcArgs a = a0;
     if (a.n_out <= 0) return;
     a.n_tiles = div_up(a.n_out, 128);
     constexpr int NP = CO < 16 ? 16 : CO;
-    constexpr size_t smem = (size_t)tc_stages(NP) * (2 * 128 * 128 + 2 * NP * 128) + 1024;
+    constexpr int STAGE = 2 * 128 * 128 + 2 * NP * 128;
     int grid = std::min(a.n_tiles, kNumSMs);
     if (f16) {
-        auto kern = k_conv_tc<CI, CO, KV, CAT, true, true, GR>;
+        constexpr int staging = tc_staging_bytes(CO, tc_bulk(CO, true, true));
+        constexpr size_t smem = (size_t)tc_stages(NP, staging) * STAGE + staging + 1024;
+        auto kern = k_conv_tc<CI, CO, KV, CAT, true, true, GR, UP>;
         SQSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, tc_threads(GR), smem, cx.st>>>(a);
-    } else if (precise) {
-        auto kern = k_conv_tc<CI, CO, KV, CAT, true, false, 2>;
-        SQSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, tc_threads(2), smem, cx.st>>>(a);
+    } else if constexpr (!UP) {
+        constexpr size_t smem = (size_t)tc_stages(NP) * STAGE + 1024;
+        if (precise) {
+            auto kern = k_conv_tc<CI, CO, KV, CAT, true, false, 2, false>;
+            SQSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, tc_threads(2), smem, cx.st>>>(a);
+        } else {
+            auto kern = k_conv_tc<CI, CO, KV, CAT, false, false, 2, false>;
+            SQSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, tc_threads(2), smem, cx.st>>>(a);
+        }
     } else {
-        auto kern = k_conv_tc<CI, CO, KV, CAT, false, false, 2>;
-        SQSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, tc_threads(2), smem, cx.st>>>(a);
+        throw CudaError("conv_tc: the inverse convolution runs in the FP16 split mode only");
     }
     cx.launches++;
 }
 
 // Dispatch on the shapes that occur in SmartTreeXX. Returns false for shapes it does not cover.
+// `fused` (nullptr or two entries): operands the epilogue writes for the consumers of this output (FP16 modes).
+// `up_parent` / `up_koff` non-null: SparseInverseConv3d(k = 2) - kv must be 8, the rulebook entry (k, row) is
+// parent[row] when koff[row] == k (every fine row has exactly one pair), nbr is ignored.
 bool conv_tc(Ctx& cx, int ci, int co, int kv, bool cat, const float* inA, const float* inB, const float* inA_lo,
              const float* inB_lo, const int32_t* nbr, const float* wimg, const float* res, const float* sel_src,
-             const uint8_t* sel_flag, float* out, int64_t n_out, bool precise, bool f16, void* out_hi, void* out_lo,
-             const float* out_bn, int* range_flag) {
+             const uint8_t* sel_flag, float* out, int64_t n_out, bool precise, bool f16, const TcFused* fused,
+             int* range_flag, const int32_t* up_parent, const int32_t* up_koff) {
     TcArgs a;
-    a.out_hi = (__half*)out_hi; a.out_lo = (__half*)out_lo; a.out_bn = out_bn; a.range_flag = range_flag;
+    for (int q = 0; q < 2; ++q) {
+        a.sp[q].hi = fused ? (__half*)fused[q].hi : nullptr;
+        a.sp[q].lo = fused ? (__half*)fused[q].lo : nullptr;
+        a.sp[q].alpha = fused ? fused[q].alpha : nullptr;
+        a.sp[q].beta = fused ? fused[q].beta : nullptr;
+    }
+    a.range_flag = range_flag;
     a.inA = inA; a.inB = inB; a.inA_lo = inA_lo; a.inB_lo = inB_lo; a.nbr = nbr; a.wimg = wimg; a.res = res; a.sel_src = sel_src; a.sel_flag = sel_flag;
+    a.up_parent = up_parent; a.up_koff = up_koff;
     a.out = out; a.n_out = (int)n_out; a.n_tiles = 0;
-#define SQSM_TC_CASE(CI_, CO_, KV_, CAT_)                                         \
-    if (ci == CI_ && co == CO_ && kv == KV_ && cat == CAT_) {                     \
-        launch_tc<CI_, CO_, KV_, CAT_>(cx, a, precise, f16);                      \
+    const bool up = up_parent != nullptr;
+#define SQSM_TC_CASE(CI_, CO_, KV_, CAT_, UP_)                                    \
+    if (ci == CI_ && co == CO_ && kv == KV_ && cat == CAT_ && up == UP_) {        \
+        launch_tc<CI_, CO_, KV_, CAT_, UP_>(cx, a, precise, f16);                 \
         return true;                                                              \
     }
-    SQSM_TC_CASE(8, 8, 27, false) SQSM_TC_CASE(16, 8, 27, true) SQSM_TC_CASE(16, 8, 1, true)
-    SQSM_TC_CASE(16, 16, 27, false) SQSM_TC_CASE(32, 32, 27, false) SQSM_TC_CASE(64, 64, 27, false)
-    SQSM_TC_CASE(32, 16, 27, true) SQSM_TC_CASE(64, 32, 27, true)
-    SQSM_TC_CASE(32, 16, 1, true) SQSM_TC_CASE(64, 32, 1, true)
-    SQSM_TC_CASE(8, 16, 8, false) SQSM_TC_CASE(16, 32, 8, false) SQSM_TC_CASE(32, 64, 8, false)
-    SQSM_TC_CASE(32, 16, 8, false) SQSM_TC_CASE(64, 32, 8, false)
+    SQSM_TC_CASE(8, 8, 27, false, false) SQSM_TC_CASE(16, 8, 27, true, false) SQSM_TC_CASE(16, 8, 1, true, false)
+    SQSM_TC_CASE(16, 16, 27, false, false) SQSM_TC_CASE(32, 32, 27, false, false) SQSM_TC_CASE(64, 64, 27, false, false)
+    SQSM_TC_CASE(32, 16, 27, true, false) SQSM_TC_CASE(64, 32, 27, true, false)
+    SQSM_TC_CASE(32, 16, 1, true, false) SQSM_TC_CASE(64, 32, 1, true, false)
+    SQSM_TC_CASE(8, 16, 8, false, false) SQSM_TC_CASE(16, 32, 8, false, false) SQSM_TC_CASE(32, 64, 8, false, false)
+    SQSM_TC_CASE(16, 8, 8, false, true) SQSM_TC_CASE(32, 16, 8, false, true) SQSM_TC_CASE(64, 32, 8, false, true)
 #undef SQSM_TC_CASE
     return false;
 }

@@ -51,6 +51,7 @@ struct sqsm_engine {
     int64_t max_entries_per_pass = 48ll << 20;
     size_t pool_reserved = 0;
     PrepState prep;
+    GraphState graph;
 };
 
 static std::string g_create_error;
@@ -654,6 +655,72 @@ extern "C" int sqsm_radius_graph_points(sqsm_handle h, const float* pts, int64_t
     DBuf<float> d(m * 3, h->cx.st);
     SQSM_CUDA(cudaMemcpyAsync(d.p, pts, sizeof(float) * m * 3, cudaMemcpyHostToDevice, h->cx.st));
     edges_out(h, d.p, m, r, n_edges, out, capacity);
+    SQSM_API_END(h)
+}
+
+// ---- connectivity graph + skeleton extraction (row a16 / f1)
+extern "C" int sqsm_graph_construct(sqsm_handle h, const float* pts, int64_t m, const int32_t* simplices, int64_t n_simplices,
+                                    double r, const int64_t* preset_edges, int64_t n_preset, int64_t* n_edges) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(simplices && n_simplices > 0 && n_edges, "bad arguments");
+    cudaStream_t st = h->cx.st;
+    DBuf<float> d_own;
+    const float* d_pts = nullptr;
+    if (pts) {                                               // caller-provided skeletal points
+        SQSM_CHECK(m > 0, "bad point count");
+        d_own.alloc(m * 3, st);
+        SQSM_CUDA(cudaMemcpyAsync(d_own.p, pts, sizeof(float) * m * 3, cudaMemcpyHostToDevice, st));
+        d_pts = d_own.p;
+    } else {                                                 // the engine's last skeletal sample
+        SQSM_CHECK(h->sk_valid, "call sqsm_skeletal_sample first (or pass the skeletal points)");
+        m = h->sk.m;
+        d_pts = h->sk.pts.p;
+    }
+    DBuf<int64_t> own_edges;
+    const int64_t* d_radius = nullptr;
+    int64_t n_radius = 0;
+    if (r > 0) {
+        ProfScope ps(h->cx, "radius_graph", (double)m * 12.0, 0.0);
+        if (pts) {
+            radius_graph(h->cx, d_pts, m, r, own_edges, &n_radius);
+            d_radius = own_edges.p;
+        } else {
+            if (h->edges_r != r) {
+                radius_graph(h->cx, d_pts, m, r, h->edges, &h->n_edges);
+                h->edges_r = r;
+            }
+            d_radius = h->edges.p;
+            n_radius = h->n_edges;
+        }
+    }
+    {
+        ProfScope ps(h->cx, "graph_construct", (double)n_simplices * 16.0 + (double)n_radius * 16.0, 0.0);
+        graph_construct(h->cx, h->graph, d_pts, m, simplices, n_simplices, d_radius, n_radius, preset_edges, n_preset);
+    }
+    *n_edges = h->graph.n_edges;
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_graph_edges(sqsm_handle h, int64_t* edges) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(edges, "null output");
+    graph_edges(h->cx, h->graph, edges);
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_graph_info(sqsm_handle h, int64_t* info5) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(h->graph.valid && info5, "no graph");
+    info5[0] = h->graph.delaunay_root; info5[1] = h->graph.n_delaunay; info5[2] = h->graph.n_spt; info5[3] = h->graph.n_mst;
+    info5[4] = h->graph.n_edges;
+    SQSM_API_END(h)
+}
+
+extern "C" int sqsm_graph_extract_skeleton(sqsm_handle h, int32_t weight_fn, int64_t* root, int64_t* n_reached, int64_t* pred,
+                                           int64_t* order, float* weight) {
+    SQSM_API_BEGIN(h)
+    ProfScope ps(h->cx, "graph_skeleton", (double)h->graph.n_edges * 16.0, 0.0);
+    graph_extract_skeleton(h->cx, h->graph, weight_fn, root, n_reached, pred, order, weight);
     SQSM_API_END(h)
 }
 

@@ -56,7 +56,6 @@ struct ConvW {                          // one convolution, device resident
     float* wimg = nullptr;              // tensor-core weight image, TF32 hi/lo (conv_tc.cu) or null
     float* wimg16 = nullptr;            // tensor-core weight image, FP16 hi/lo
     float* wimg_tma = nullptr;          // weight image of the TMA-gather kernel (conv_tma.cu) or null
-    float* wimg_up = nullptr;           // inverse convolutions: FP16 image of the dense [ci][8*co] GEMM (upconv_tc.cu)
 };
 
 struct HeadW {                          // output_layer BN + both MLP heads; index 0 = offset, 1 = regression
@@ -83,6 +82,15 @@ struct NetWeights {
 constexpr int kTmZeroRows = 1024;        // rows of zeros behind every split-row array (absent neighbours, conv_tma.cu)
 
 struct Net;                             // conv.cu
+
+// Operands a tensor-core epilogue writes for ONE consumer of its output: FP16 hi / lo split of relu(out * alpha + beta)
+// (alpha == nullptr: of the raw output).  conv_tc.cu.
+struct TcFused {
+    void* hi = nullptr;
+    void* lo = nullptr;
+    const float* alpha = nullptr;
+    const float* beta = nullptr;
+};
 
 // conv.cu
 void net_upload(Ctx& cx, NetWeights& nw, const std::map<std::string, std::vector<float>>& state, bool down_flip);
@@ -127,6 +135,23 @@ struct SkeletalResult {
 };
 void skeletal_sample(Ctx& cx, const float* d_P, const float* d_D, int64_t n, double voxel, SkeletalResult& out);
 void radius_graph(Ctx& cx, const float* d_pts, int64_t m, double r, DBuf<int64_t>& edges, int64_t* n_edges);
+
+// graph.cu (row a16 / f1: core/skeletonization_pipeline_base.py:75-238)
+struct GraphState {
+    DBuf<float> pts;                    // [m][3] skeletal points
+    std::vector<float> h_pts;
+    int64_t m = 0;
+    DBuf<uint64_t> merged;              // merged edge keys (u << 32 | v, u < v), lexicographic (:158)
+    int64_t n_edges = 0;
+    int64_t delaunay_root = -1;
+    int64_t n_spt = 0, n_mst = 0, n_delaunay = 0;
+    bool valid = false;
+};
+void graph_construct(Ctx& cx, GraphState& gs, const float* d_pts, int64_t m, const int32_t* h_simplices, int64_t T,
+                     const int64_t* d_radius, int64_t n_radius, const int64_t* h_preset, int64_t n_preset);
+void graph_edges(Ctx& cx, const GraphState& gs, int64_t* h_out);
+void graph_extract_skeleton(Ctx& cx, const GraphState& gs, int weight_fn, int64_t* root_out, int64_t* n_reached, int64_t* h_pred,
+                            int64_t* h_order, float* h_weight);
 
 // preprocess.cu (row f2: entrypoints/smartqsm.py:882-913)
 struct PrepState {
