@@ -232,6 +232,9 @@ int  sqsm_profile_families(sqsm_handle h, char* buf, int64_t capacity);   /* com
 int  sqsm_timer_start(sqsm_handle h);
 int  sqsm_timer_stop(sqsm_handle h, double* elapsed_ms);
 int  sqsm_launch_count(sqsm_handle h, int64_t* kernels_launched_since_create);
+/* The handle's CUDA stream (cudaStream_t): a caller that exchanges segments between ranks (sqsm_step_*) enqueues its
+ * collectives relative to it (e.g. torch.cuda.ExternalStream) instead of synchronising the device. */
+int  sqsm_get_stream(sqsm_handle h, void** cuda_stream);
 /* sizeof() of the public structs as the library was compiled: 0 SqsmConfig, 1 SqsmIterStats, 2 SqsmPrepConfig,
  * 3 SqsmPrepStats (-1 otherwise) - lets a binding verify its own declarations without a GPU. */
 int  sqsm_sizeof(int32_t which);

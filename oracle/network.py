@@ -218,15 +218,31 @@ class ForwardTrace:
     """Integer side products of one forward, kept for rulebook parity tests."""
     levels: List[LevelTrace] = field(default_factory=list)
     feats: Dict[str, torch.Tensor] = field(default_factory=dict)
+    # output of every sparse convolution keyed by the reference module name ("unet.u.conv.2", ...): what a forward hook on
+    # the genuine spconv layers records (scripts/reference_dump.py); filled only when keep=True
+    taps: Optional[Dict[str, torch.Tensor]] = None
+    tap_indices: Optional[Dict[str, np.ndarray]] = None
 
 
-def _residual_block(x, w: Weights, prefix: str, nbr, c_in: int, c_out: int) -> torch.Tensor:
+def _tap(trace: Optional["ForwardTrace"], name: str, feats: torch.Tensor, indices: np.ndarray) -> None:
+    if trace is not None and trace.taps is not None:
+        trace.taps[name] = feats.clone()
+        trace.tap_indices[name] = indices
+
+
+def _residual_block(x, w: Weights, prefix: str, nbr, c_in: int, c_out: int, trace=None, indices=None) -> torch.Tensor:
     """``ResidualBlock.forward`` (sparse_module.py:32-39; ctor :11-30)."""
-    ident = x if c_in == c_out else subm_conv(x, w[prefix + ".i_branch.0.weight"], nbr)
+    if c_in == c_out:
+        ident = x
+    else:
+        ident = subm_conv(x, w[prefix + ".i_branch.0.weight"], nbr)
+        _tap(trace, prefix + ".i_branch.0", ident, indices)
     y = _bn_relu(x, w, prefix + ".conv_branch.0")
     y = subm_conv(y, w[prefix + ".conv_branch.2.weight"], nbr)
+    _tap(trace, prefix + ".conv_branch.2", y, indices)
     y = _bn_relu(y, w, prefix + ".conv_branch.3")
     y = subm_conv(y, w[prefix + ".conv_branch.5.weight"], nbr)
+    _tap(trace, prefix + ".conv_branch.5", y, indices)
     return y + ident
 
 
@@ -238,7 +254,7 @@ def _ublock(x, indices, spatial_shape, w: Weights, prefix: str, planes: List[int
     lt = LevelTrace(indices, [int(s) for s in spatial_shape], nbr)
     trace.levels.append(lt)
     lvl = len(trace.levels) - 1
-    x = _residual_block(x, w, prefix + ".blocks.block0", nbr, planes[0], planes[0])
+    x = _residual_block(x, w, prefix + ".blocks.block0", nbr, planes[0], planes[0], trace, indices)
     if keep:
         trace.feats[f"enc{lvl}"] = x.clone()
     if len(planes) > 1 and safe_to_downsample(indices, spatial_shape):
@@ -246,11 +262,13 @@ def _ublock(x, indices, spatial_shape, w: Weights, prefix: str, planes: List[int
         lt.down, lt.descended = rb, True
         y = _bn_relu(x, w, prefix + ".conv.0")
         y = down_conv(y, w[prefix + ".conv.2.weight"], rb)
+        _tap(trace, prefix + ".conv.2", y, rb.coarse_indices)
         y = _ublock(y, rb.coarse_indices, rb.coarse_shape, w, prefix + ".u", planes[1:], trace, keep)
         y = _bn_relu(y, w, prefix + ".deconv.0")
         y = inverse_conv(y, w[prefix + ".deconv.2.weight"], rb)
+        _tap(trace, prefix + ".deconv.2", y, indices)
         x = torch.cat((x, y), dim=1)                          # :114
-        x = _residual_block(x, w, prefix + ".blocks_tail.block0", nbr, 2 * planes[0], planes[0])
+        x = _residual_block(x, w, prefix + ".blocks_tail.block0", nbr, 2 * planes[0], planes[0], trace, indices)
         if keep:
             trace.feats[f"dec{lvl}"] = x.clone()
     return x
@@ -272,9 +290,12 @@ def forward(feats: np.ndarray, indices: np.ndarray, spatial_shape, w: Weights,
     Returns ``(direction [N,3], distance [N,1], ForwardTrace)``.
     """
     trace = ForwardTrace()
+    if keep:
+        trace.taps, trace.tap_indices = {}, {}
     x = torch.as_tensor(feats).to(w.dtype)
     nbr0 = subm_rulebook(indices, spatial_shape)
     x = subm_conv(x, w["input_conv.0.weight"], nbr0)                               # :65
+    _tap(trace, "input_conv.0", x, indices)
     if keep:
         trace.feats["input_conv"] = x.clone()
     x = _ublock(x, indices, spatial_shape, w, "unet", list(planes), trace, keep, nbr0)  # :66 (same indice_key "subm1")

@@ -71,7 +71,7 @@ EXPORTS = [
     "sqsm_debug_batch_shapes", "sqsm_debug_level_tables", "sqsm_debug_canon_to_internal",
     "sqsm_debug_predictions", "sqsm_debug_features", "sqsm_profile_reset", "sqsm_profile_get",
     "sqsm_profile_enable", "sqsm_profile_families", "sqsm_timer_start", "sqsm_timer_stop", "sqsm_launch_count",
-    "sqsm_graph_construct", "sqsm_graph_edges", "sqsm_graph_info", "sqsm_graph_extract_skeleton",
+    "sqsm_get_stream", "sqsm_graph_construct", "sqsm_graph_edges", "sqsm_graph_info", "sqsm_graph_extract_skeleton",
     "sqsm_prepare_cloud_f64", "sqsm_prepared_size", "sqsm_get_prepared", "sqsm_set_points_prepared", "sqsm_debug_prepared", "sqsm_sizeof",
 ]
 
@@ -132,6 +132,7 @@ def load_library() -> C.CDLL:
         "sqsm_set_points_prepared": ([vp], C.c_int),
         "sqsm_debug_prepared": ([vp, vp, vp, vp], C.c_int),
         "sqsm_sizeof": ([i32], C.c_int),
+        "sqsm_get_stream": ([vp, P(vp)], C.c_int),
         "sqsm_graph_construct": ([vp, vp, i64, vp, i64, f64, vp, i64, P(i64)], C.c_int),
         "sqsm_graph_edges": ([vp, vp], C.c_int),
         "sqsm_graph_info": ([vp, vp], C.c_int),
@@ -460,6 +461,12 @@ class Engine:
         ms = C.c_double()
         self._check(self._lib.sqsm_timer_stop(self._h, C.byref(ms)), "timer_stop")
         return ms.value
+
+    def stream_ptr(self) -> int:
+        """The engine's ``cudaStream_t`` as an integer (for ``torch.cuda.ExternalStream``)."""
+        p = C.c_void_p()
+        self._check(self._lib.sqsm_get_stream(self._h, C.byref(p)), "get_stream")
+        return int(p.value or 0)
 
     def launch_count(self) -> int:
         n = C.c_int64()

@@ -57,6 +57,9 @@ struct TcArgs {
     int* range_flag;
     int n_out;
     int n_tiles;
+    int n_stages;             // ring depth actually used (<= what fits; tuning knob SQSM_TC_STAGES)
+    int contig;               // 1: a CTA takes a contiguous range of tiles (spatial neighbours: L1 / L2 reuse), 0: strided
+    int l1_alloc;             // 1: gather with cp.async.ca (allocate in L1), 0: cp.async.cg
 };
 
 constexpr int kTcMaxStages = 6;       // shared-memory ring (A hi/lo + B hi/lo per stage), as many as fit 227 KB
@@ -96,7 +99,8 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
     constexpr int B_BYTES = NP * 128;
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     constexpr bool BULK = tc_bulk(CO, F16, PRECISE);
-    constexpr int kTcStages = tc_stages(NP, tc_staging_bytes(CO, BULK));
+    constexpr int kTcStagesMax = tc_stages(NP, tc_staging_bytes(CO, BULK));   // staging tiles sit behind the full ring
+    const int kTcStages = a.n_stages;
     constexpr uint32_t FMT = F16 ? 0u : 2u;           // a/b format: F16 = 0, TF32 = 2 (UMMA::F16F32Format)
     constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     // PRECISE: the hi and lo weight tiles are adjacent in shared memory ([NP rows][128 B] each), so ONE instruction with
@@ -117,7 +121,7 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
     const uint32_t tfull0 = smem_u32(&bars[2 * kTcMaxStages]), tempty0 = smem_u32(&bars[2 * kTcMaxStages + 2]);
 
     if (t == 0) {
-        for (int s = 0; s < kTcStages; ++s) { mbar_init(full0 + 8 * s, kTcProducers); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < kTcStagesMax; ++s) { mbar_init(full0 + 8 * s, kTcProducers); mbar_init(empty0 + 8 * s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, kTcEpilogue); }
         mbar_init(smem_u32(&bars[2 * kTcMaxStages + 4]), 1);      // residual tile landed (bulk epilogue)
         fence_barrier_init();
@@ -127,12 +131,17 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    // tiles of this CTA: strided over the grid, or one contiguous range (neighbouring tiles share gathered rows)
+    const int t_per = (a.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int t_first = a.contig ? (int)blockIdx.x * t_per : (int)blockIdx.x;
+    const int t_stride = a.contig ? 1 : (int)gridDim.x;
+    const int t_count = a.contig ? max(0, min(t_per, a.n_tiles - t_first)) : (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (warp < kTcProdWarps) {
         // ===================== producers: rulebook rows -> cp.async gather into the swizzled smem tiles =====================
         // Nothing but rulebook entries passes through registers: the pre-split operands go global -> shared by LDGSTS and
         // the stage's mbarrier counts their arrival.
-        const int n_my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int n_my_tiles = t_count;
         const int total = n_my_tiles * NCH;               // chunk sequence of this CTA
         const int grp = warp >> 2;                        // producer group
         const int tp = t & (kTcProducers - 1);            // thread inside the group = tile row
@@ -148,7 +157,7 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
         int ibuf[RI][KPC];
         auto issue_idx = [&](int i, int* nb) {            // i-th chunk of this group
             const int c = grp + i * kTcGroups;
-            const int tile = (int)blockIdx.x + (c / NCH) * (int)gridDim.x;
+            const int tile = t_first + (c / NCH) * t_stride;
             const int j = c % NCH;
             const int row = tile * 128 + tp;
             #pragma unroll
@@ -173,7 +182,7 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
                 const int i = i0 + u;
                 if (i < my_total) {
                     const int c = grp + i * kTcGroups;
-                    const uint32_t stage = (uint32_t)c % kTcStages, ph = ((uint32_t)c / kTcStages) & 1u;
+                    const uint32_t stage = (uint32_t)c % (uint32_t)kTcStages, ph = ((uint32_t)c / (uint32_t)kTcStages) & 1u;
                     const int j = c % NCH;
                     const uint32_t sA_hi = smem_base + stage * STAGE_BYTES;
                     const uint32_t sA_lo = sA_hi + A_BYTES;
@@ -200,8 +209,13 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
                         const uint32_t off = rt * 128u + (uint32_t)((piece ^ (int)(rt & 7u)) << 4);
                         const uint32_t sz = on ? 16u : 0u;
                         // element offsets are in operand elements (float or __half)
-                        cp_async16(sA_hi + off, (const char*)(second ? a.inB : a.inA) + eoff * ES, sz);
-                        if (PRECISE) cp_async16(sA_lo + off, (const char*)(second ? a.inB_lo : a.inA_lo) + eoff * ES, sz);
+                        if (a.l1_alloc) {
+                            cp_async16_ca(sA_hi + off, (const char*)(second ? a.inB : a.inA) + eoff * ES, sz);
+                            if (PRECISE) cp_async16_ca(sA_lo + off, (const char*)(second ? a.inB_lo : a.inA_lo) + eoff * ES, sz);
+                        } else {
+                            cp_async16(sA_hi + off, (const char*)(second ? a.inB : a.inA) + eoff * ES, sz);
+                            if (PRECISE) cp_async16(sA_lo + off, (const char*)(second ? a.inB_lo : a.inA_lo) + eoff * ES, sz);
+                        }
                     }
                     {   // weight chunk: hi tile then lo tile, already swizzled images (L2 resident)
                         const float* src = a.wimg + (size_t)j * (2 * B_BYTES / 4);
@@ -221,12 +235,13 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
         // ===================== epilogue: TMEM -> registers -> residual / select -> global =====================
         const int te = t - kTcGroups * kTcProducers;      // tile row, also the TMEM lane
         // staging tiles of the bulk epilogue, behind the stage ring (row-major like global memory: one bulk copy per tile)
-        float* const out_s = reinterpret_cast<float*>(smem + (size_t)kTcStages * STAGE_BYTES);
+        float* const out_s = reinterpret_cast<float*>(smem + (size_t)kTcStagesMax * STAGE_BYTES);
         float* const res_s = out_s + 128 * CO;
         __half* const sp_s = reinterpret_cast<__half*>(res_s + 128 * CO);      // [2 splits][hi, lo][128][CO]
         const uint32_t res_bar = smem_u32(&bars[2 * kTcMaxStages + 4]);
-        uint32_t tile_it = 0, res_it = 0;
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tile_it) {
+        uint32_t res_it = 0;
+        for (uint32_t tile_it = 0; tile_it < (uint32_t)t_count; ++tile_it) {
+            const int tile = t_first + (int)tile_it * t_stride;
             const uint32_t as = tile_it & 1u, aph = (tile_it >> 1) & 1u;
             const int row = tile * 128 + te;
             const bool live = row < a.n_out;
@@ -335,15 +350,15 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
         if (BULK && te == 0) bulk_wait_all();               // stores complete before the shared memory goes away
     } else if ((t & 31) == 0) {
         // ===================== MMA issuer: one thread =====================
-        uint32_t it = 0, tile_it = 0;
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tile_it) {
+        uint32_t it = 0;
+        for (uint32_t tile_it = 0; tile_it < (uint32_t)t_count; ++tile_it) {
             const uint32_t as = tile_it & 1u, aph = (tile_it >> 1) & 1u;
             mbar_wait(tempty0 + 8 * as, aph ^ 1u);      // epilogue has drained this accumulator stage
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + as * ACC;
             #pragma unroll 1
             for (int j = 0; j < NCH; ++j, ++it) {
-                const uint32_t stage = it % kTcStages, ph = (it / kTcStages) & 1u;
+                const uint32_t stage = it % (uint32_t)kTcStages, ph = (it / (uint32_t)kTcStages) & 1u;
                 mbar_wait(full0 + 8 * stage, ph);
                 fence_proxy_async();                    // cp.async wrote through the generic proxy; the MMA reads through the async proxy
                 tc_fence_after();
@@ -495,17 +510,27 @@ static void launch_tc(Ctx& cx, const TcArgs& a0, bool precise, bool f16) {
     TcArgs a = a0;
     if (a.n_out <= 0) return;
     a.n_tiles = div_up(a.n_out, 128);
+    static const int env_stages = [] { const char* e = getenv("SQSM_TC_STAGES"); return e ? atoi(e) : 0; }();
+    static const int env_contig = [] { const char* e = getenv("SQSM_TC_CONTIG"); return e ? atoi(e) : 0; }();
+    static const int env_ca = [] { const char* e = getenv("SQSM_TC_CA"); return e ? atoi(e) : 0; }();
+    a.contig = env_contig;
+    a.l1_alloc = env_ca;
     constexpr int NP = CO < 16 ? 16 : CO;
     constexpr int STAGE = 2 * 128 * 128 + 2 * NP * 128;
     int grid = std::min(a.n_tiles, kNumSMs);
     if (f16) {
         constexpr int staging = tc_staging_bytes(CO, tc_bulk(CO, true, true));
         constexpr size_t smem = (size_t)tc_stages(NP, staging) * STAGE + staging + 1024;
+        a.n_stages = tc_stages(NP, staging);
+        // at least as many stages as producer groups: with fewer, a group gets two ring cycles ahead of a stage's "empty"
+        // barrier and its parity wait is satisfied by the stale phase (corrupt tiles or a hang)
+        if (env_stages > 0) a.n_stages = std::max(GR, std::min(env_stages, a.n_stages));
         auto kern = k_conv_tc<CI, CO, KV, CAT, true, true, GR, UP>;
         SQSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, tc_threads(GR), smem, cx.st>>>(a);
     } else if constexpr (!UP) {
         constexpr size_t smem = (size_t)tc_stages(NP) * STAGE + 1024;
+        a.n_stages = tc_stages(NP);
         if (precise) {
             auto kern = k_conv_tc<CI, CO, KV, CAT, true, false, 2, false>;
             SQSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

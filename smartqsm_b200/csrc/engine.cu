@@ -930,6 +930,13 @@ extern "C" int sqsm_timer_stop(sqsm_handle h, double* ms) {
     SQSM_API_END(h)
 }
 
+extern "C" int sqsm_get_stream(sqsm_handle h, void** stream) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(stream, "null argument");
+    *stream = (void*)h->cx.st;
+    SQSM_API_END(h)
+}
+
 extern "C" int sqsm_launch_count(sqsm_handle h, int64_t* n) {
     SQSM_API_BEGIN(h)
     SQSM_CHECK(n, "null argument");

@@ -9,6 +9,7 @@
 // All three run on the BrickMap: an 8-voxel brick is the search cell; exact nearest neighbours
 // are found by growing rings of bricks until the best distance is below the ring's lower bound.
 #include "engine.h"
+#include <cub/cub.cuh>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -96,6 +97,8 @@ __global__ void __launch_bounds__(256) k_grid_entries(const float* __restrict__ 
 struct GridMap {
     BrickMap map;
     DBuf<int32_t> pt_row;      // [n] voxel row of every point
+    DBuf<int32_t> ent_brick;   // [n] brick of every point (-1: outside the grid)
+    DBuf<uint16_t> ent_pos;    // [n] voxel position inside the brick
     GridParams g;
 };
 
@@ -112,17 +115,17 @@ static void grid_build(Ctx& cx, const float* d_P, int64_t n, const double mn[3],
     for (int a = 0; a < 3; ++a) gm.g.mn[a] = mn[a];
     gm.g.voxel = voxel;
     DBuf<uint64_t> ent_key(n, st);
-    DBuf<uint16_t> ent_pos(n, st);
-    DBuf<int32_t> ent_brick(n, st);
+    gm.ent_pos.alloc(n, st);
+    gm.ent_brick.alloc(n, st);
     DBuf<int32_t> err(1, st);
     err.zero();
-    k_grid_entries<<<div_up(n, 256), 256, 0, st>>>(d_P, n, gm.g, ent_key.p, ent_pos.p, err.p);
+    k_grid_entries<<<div_up(n, 256), 256, 0, st>>>(d_P, n, gm.g, ent_key.p, gm.ent_pos.p, err.p);
     cx.launches++;
-    brickmap_build(cx, gm.map, ent_key.p, ent_pos.p, n, ent_brick.p);
+    brickmap_build(cx, gm.map, ent_key.p, gm.ent_pos.p, n, gm.ent_brick.p);
     int32_t herr = 0;
     SQSM_CUDA(cudaMemcpyAsync(&herr, err.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     gm.pt_row.alloc(n, st);
-    k_point_rows<<<div_up(n, 256), 256, 0, st>>>(gm.map.bricks.p, ent_brick.p, ent_pos.p, n, gm.pt_row.p);
+    k_point_rows<<<div_up(n, 256), 256, 0, st>>>(gm.map.bricks.p, gm.ent_brick.p, gm.ent_pos.p, n, gm.pt_row.p);
     cx.launches++;
     SQSM_CUDA(cudaStreamSynchronize(st));
     SQSM_CHECK(herr == 0, "cloud extent exceeds 524288 voxels per axis (or NaN coordinates)");
@@ -130,62 +133,151 @@ static void grid_build(Ctx& cx, const float* d_P, int64_t n, const double mn[3],
 
 // ---------------------------------------------------------------------------------- Chamfer monitor
 
+// Voxel means (Open3D AccumulatedPoint: sum / count).  Order-independent and therefore bit-reproducible: every point adds
+// its offset from the origin of its OWN voxel, in fixed point (2^-58 m: the offset is below one voxel edge, so even 2^20
+// points per voxel cannot overflow 63 bits for edges up to 0.5 m), with 64-bit integer atomics; the mean is the origin
+// plus the exactly accumulated offset sum over the count, rounded once.  Open3D's sequential float64 sum differs from it
+// by its own rounding only (<= ~1e-15 m).
+constexpr double kFixScale = 288230376151711744.0;               // 2^58
+
+__device__ __forceinline__ void voxel_origin(const Brick* __restrict__ bricks, int brick, uint32_t pos, const GridParams& g,
+                                             double o[3]) {
+    const uint64_t key = bricks[brick].key;
+    o[0] = g.mn[0] + (double)((int)key_x(key) * 8 + (int)(pos & 7u)) * g.voxel;
+    o[1] = g.mn[1] + (double)((int)key_y(key) * 8 + (int)((pos >> 3) & 7u)) * g.voxel;
+    o[2] = g.mn[2] + (double)((int)key_z(key) * 8 + (int)(pos >> 6)) * g.voxel;
+}
+
 __global__ void __launch_bounds__(256) k_voxel_accumulate(const float* __restrict__ P, const int32_t* __restrict__ pt_row,
-                                                          int64_t n, double* __restrict__ sum, int32_t* __restrict__ cnt) {
+                                                          const int32_t* __restrict__ ent_brick, const uint16_t* __restrict__ ent_pos,
+                                                          const Brick* __restrict__ bricks, const __grid_constant__ GridParams g,
+                                                          int64_t n, long long* __restrict__ sum, int32_t* __restrict__ cnt) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int r = pt_row[i];
     if (r < 0) return;
-    atomicAdd(&sum[3 * (size_t)r + 0], (double)P[3 * i + 0]);
-    atomicAdd(&sum[3 * (size_t)r + 1], (double)P[3 * i + 1]);
-    atomicAdd(&sum[3 * (size_t)r + 2], (double)P[3 * i + 2]);
+    double o[3];
+    voxel_origin(bricks, ent_brick[i], ent_pos[i], g, o);
+    #pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const long long q = __double2ll_rn(((double)P[3 * i + a] - o[a]) * kFixScale);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&sum[3 * (size_t)r + a]), (unsigned long long)q);
+    }
     atomicAdd(&cnt[r], 1);
 }
 
-__global__ void __launch_bounds__(256) k_voxel_mean(double* __restrict__ sum, const int32_t* __restrict__ cnt, int64_t rows) {
+// mean (float64) and the float32 copy relative to the brick origin (screening copy of the NN search) in one pass
+__global__ void __launch_bounds__(256) k_voxel_mean(const long long* __restrict__ sum, const int32_t* __restrict__ cnt,
+                                                    const int32_t* __restrict__ row_brick, const uint16_t* __restrict__ row_pos,
+                                                    const Brick* __restrict__ bricks, const __grid_constant__ GridParams g,
+                                                    int64_t rows, double* __restrict__ mean, float4* __restrict__ loc) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
-    double c = (double)cnt[r];
-    sum[3 * r + 0] = __ddiv_rn(sum[3 * r + 0], c);
-    sum[3 * r + 1] = __ddiv_rn(sum[3 * r + 1], c);
-    sum[3 * r + 2] = __ddiv_rn(sum[3 * r + 2], c);
-}
-
-// voxel means relative to the origin of their own brick, float32 (screening copy for the NN search)
-__global__ void __launch_bounds__(256) k_local_means(const Brick* __restrict__ bricks, int n_bricks, const double* __restrict__ mean,
-                                                     const __grid_constant__ GridParams g, float4* __restrict__ loc) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int b = t >> 5, lane = t & 31;
-    if (b >= n_bricks) return;
-    const uint64_t key = bricks[b].key;
+    const int b = row_brick[r];
+    const uint32_t pos = row_pos[r];
+    double o[3];
+    voxel_origin(bricks, b, pos, g, o);
+    const double c = (double)cnt[r] * kFixScale;
     const double edge = 8.0 * g.voxel;
-    const double ox = g.mn[0] + (double)key_x(key) * edge, oy = g.mn[1] + (double)key_y(key) * edge,
-                 oz = g.mn[2] + (double)key_z(key) * edge;
-    const int base = bricks[b].base, n = bricks[b].count;
-    for (int i = lane; i < n; i += 32) {
-        const size_t r = (size_t)(base + i);
-        loc[r] = make_float4((float)(mean[3 * r] - ox), (float)(mean[3 * r + 1] - oy), (float)(mean[3 * r + 2] - oz), 0.f);
+    const uint64_t key = bricks[b].key;
+    const double bo[3] = {g.mn[0] + (double)key_x(key) * edge, g.mn[1] + (double)key_y(key) * edge, g.mn[2] + (double)key_z(key) * edge};
+    double m[3];
+    #pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        m[a] = o[a] + __ddiv_rn((double)sum[3 * r + a], c);
+        mean[3 * r + a] = m[a];
     }
+    loc[r] = make_float4((float)(m[0] - bo[0]), (float)(m[1] - bo[1]), (float)(m[2] - bo[2]), 0.f);
 }
 
 // For every brick of map A: (first row, count) of the 27 bricks of map B around the same coordinates.
 __global__ void __launch_bounds__(256) k_cross_neighbours(const Brick* __restrict__ A, int nA, BrickHash hB,
-                                                          const Brick* __restrict__ B, int2* __restrict__ abn) {
+                                                          const Brick* __restrict__ B, int2* __restrict__ abn,
+                                                          int32_t* __restrict__ abid) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int a = t >> 5, j = t & 31;
     if (a >= nA) return;
     int2 r = make_int2(0, 0);
+    int id = -1;
     if (j < 27) {
         uint64_t key = A[a].key;
         int z = (int)key_z(key) + j / 9 - 1, y = (int)key_y(key) + (j / 3) % 3 - 1, x = (int)key_x(key) + j % 3 - 1;
         if (z >= 0 && y >= 0 && x >= 0 && z < 65536 && y < 65536 && x < 65536) {
-            int id = hash_find(hB, pack_key(0u, (uint32_t)z, (uint32_t)y, (uint32_t)x));
+            id = hash_find(hB, pack_key(0u, (uint32_t)z, (uint32_t)y, (uint32_t)x));
             if (id >= 0) r = make_int2(B[id].base, B[id].count);
         }
     }
+    abid[(size_t)a * 32 + j] = id;                                                    // brick ids (cell-ring search)
     const unsigned present = __ballot_sync(0xFFFFFFFFu, r.y > 0);
     if (j == 27) r.x = (int)present;                                                 // entry 27: which of the 27 exist
     abn[(size_t)a * 32 + j] = r;
+}
+
+// First stage of the exact 1-NN search: both clouds live on the SAME voxel grid (:116-121), a voxel mean lies inside its
+// voxel, so the candidates of a query are enumerated by growing cubes of voxel CELLS around the query's own cell, read
+// straight from the occupancy bitmaps of B's bricks (one 8-bit row of a brick line per (z, y) row, a popcount gives the
+// row of an occupied cell).  After the (2R+1)^3 cube every unseen mean is farther than the query's distance to the faces
+// of that cube; if the best candidate is closer (minus 1 nm of slack for the rounding of means on cell faces) the query
+// is settled - about half of them at R = 2 (~20 candidates instead of the ~110 of a brick-level search).  Unsettled
+// queries are appended to a list for the next stage.  One thread per query; neighbouring queries share bricks (L1 hits).
+template <int R>
+__global__ void __launch_bounds__(256) k_nn_cells(const Brick* __restrict__ A, const int32_t* __restrict__ row_brick,
+                                                  const uint16_t* __restrict__ row_pos, const int32_t* __restrict__ list,
+                                                  int64_t n, const double* __restrict__ meanA, const int32_t* __restrict__ abid,
+                                                  const Brick* __restrict__ B, const double* __restrict__ meanB,
+                                                  const __grid_constant__ GridParams g, int shard, int n_shards,
+                                                  double* __restrict__ nn2, int32_t* __restrict__ unsettled,
+                                                  int32_t* __restrict__ n_unsettled) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int64_t r = list ? (int64_t)list[idx] : idx;
+    const int a = row_brick[r];
+    if (n_shards > 1 && (a % n_shards) != shard) return;
+    const uint32_t pos = row_pos[r];
+    const int z = (int)(pos >> 6), y = (int)(pos >> 3) & 7, x = (int)pos & 7;
+    const double qx = meanA[3 * r], qy = meanA[3 * r + 1], qz = meanA[3 * r + 2];
+    const int32_t* __restrict__ ids = abid + (size_t)a * 32;
+    double best = 1e300;
+    #pragma unroll 1
+    for (int dz = -R; dz <= R; ++dz) {
+        const int zz = z + dz, bzo = zz < 0 ? 0 : (zz > 7 ? 2 : 1), zl = zz & 7;
+        #pragma unroll 1
+        for (int dy = -R; dy <= R; ++dy) {
+            const int yy = y + dy, byo = yy < 0 ? 0 : (yy > 7 ? 2 : 1), yl = yy & 7;
+            const int w = zl * 2 + (yl >> 2), sh = (yl & 3) * 8;
+            #pragma unroll
+            for (int seg = 0; seg < 3; ++seg) {
+                int lo, hi;                                       // x range inside brick column seg (0 left, 1 own, 2 right)
+                if (seg == 0) { lo = x - R + 8; hi = 7; }
+                else if (seg == 1) { lo = max(0, x - R); hi = min(7, x + R); }
+                else { lo = 0; hi = x + R - 8; }
+                if (lo > hi) continue;
+                const int id = ids[bzo * 9 + byo * 3 + seg];
+                if (id < 0) continue;
+                const Brick* __restrict__ b = &B[id];
+                const uint32_t word = b->mask[w];
+                uint32_t bits = (word >> sh) & 0xFFu & (((1u << (hi - lo + 1)) - 1u) << lo);
+                if (!bits) continue;
+                const int rbase = b->base + (int)b->prefix[w];
+                while (bits) {
+                    const int bit = sh + __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const size_t row = (size_t)(rbase + __popc(word & ((1u << bit) - 1u)));
+                    const double ex = qx - meanB[3 * row], ey = qy - meanB[3 * row + 1], ez = qz - meanB[3 * row + 2];
+                    best = fmin(best, ex * ex + ey * ey + ez * ez);
+                }
+            }
+        }
+    }
+    // distance from the query to the outside of the scanned cube of cells
+    const uint64_t key = A[a].key;
+    const int cx = (int)key_x(key) * 8 + x, cy = (int)key_y(key) * 8 + y, cz = (int)key_z(key) * 8 + z;
+    double lb = fmin(qx - (g.mn[0] + (double)(cx - R) * g.voxel), (g.mn[0] + (double)(cx + R + 1) * g.voxel) - qx);
+    lb = fmin(lb, fmin(qy - (g.mn[1] + (double)(cy - R) * g.voxel), (g.mn[1] + (double)(cy + R + 1) * g.voxel) - qy));
+    lb = fmin(lb, fmin(qz - (g.mn[2] + (double)(cz - R) * g.voxel), (g.mn[2] + (double)(cz + R + 1) * g.voxel) - qz));
+    lb -= 1e-9;
+    if (lb > 0.0 && best <= lb * lb) nn2[r] = best;
+    else unsettled[atomicAdd(n_unsettled, 1)] = (int32_t)r;
 }
 
 // Exact 1-NN squared distances from the voxel means of map A to those of map B, summed.
@@ -206,6 +298,7 @@ struct NNWarpShared {
     float4 ql[32];
     unsigned long long best[32];
     int brick[32];
+    int row[32];
     uint16_t list[32 * 20];
 };
 __device__ __forceinline__ float nn_gap2(int nb, const float* gm2, const float* gp2) {
@@ -214,15 +307,17 @@ __device__ __forceinline__ float nn_gap2(int nb, const float* gm2, const float* 
             (dz == 0 ? 0.f : (dz < 0 ? gm2[2] : gp2[2]))) * 0.999999f;
 }
 __global__ void __launch_bounds__(256) k_nn_sqdist_pairs(const Brick* __restrict__ A, const int32_t* __restrict__ row_brick,
-                                                         int64_t n_rows, const double* __restrict__ meanA,
+                                                         const int32_t* __restrict__ qlist, int64_t n_rows,
+                                                         const double* __restrict__ meanA,
                                                          const float4* __restrict__ locA, const int2* __restrict__ abn,
                                                          BrickHash hB, const Brick* __restrict__ B,
                                                          const double* __restrict__ meanB, const float4* __restrict__ locB,
                                                          const __grid_constant__ GridParams g, int max_ring, int shard,
-                                                         int n_shards, double* __restrict__ acc,
+                                                         int n_shards, double* __restrict__ nn2,
                                                          unsigned long long* __restrict__ n_fallback) {
+    // queries = the rows listed in qlist (n_rows entries; unsettled by the cell-ring stages) or all rows 0 .. n_rows-1;
+    // the exact squared 1-NN distance of query row r goes to nn2[r]
     __shared__ NNWarpShared s_warp[8];
-    __shared__ double s_red[8];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     NNWarpShared& S = s_warp[w];
     const double edge = 8.0 * g.voxel;
@@ -231,11 +326,10 @@ __global__ void __launch_bounds__(256) k_nn_sqdist_pairs(const Brick* __restrict
     constexpr unsigned kRoundMask[3] = {1u << 13,
                                         (1u << 4) | (1u << 10) | (1u << 12) | (1u << 14) | (1u << 16) | (1u << 22),
                                         0x07FFFFFFu & ~((1u << 13) | (1u << 4) | (1u << 10) | (1u << 12) | (1u << 14) | (1u << 16) | (1u << 22))};
-    double local_sum = 0.0;
     unsigned fb = 0;
     for (int64_t base = ((int64_t)blockIdx.x * 8 + w) * 32; base < n_rows; base += (int64_t)gridDim.x * 256) {
-        const int64_t r = base + lane;
-        bool valid = r < n_rows;
+        bool valid = base + lane < n_rows;
+        const int64_t r = valid ? (qlist ? (int64_t)qlist[base + lane] : base + lane) : 0;
         const int a = valid ? row_brick[r] : 0;
         if (n_shards > 1 && (a % n_shards) != shard) valid = false;
         if (!__any_sync(0xFFFFFFFFu, valid)) continue;
@@ -248,6 +342,7 @@ __global__ void __launch_bounds__(256) k_nn_sqdist_pairs(const Brick* __restrict
         __syncwarp();
         S.ql[lane] = ql;
         S.brick[lane] = a;
+        S.row[lane] = (int)r;
         S.best[lane] = (unsigned long long)__double_as_longlong(1e300);
         double best = 1e300;
         #pragma unroll 1
@@ -296,7 +391,7 @@ __global__ void __launch_bounds__(256) k_nn_sqdist_pairs(const Brick* __restrict
                     const int2 rc = abn[(size_t)S.brick[o] * 32 + nb];
                     const int dz = nb / 9 - 1, dy = (nb / 3) % 3 - 1, dx = nb % 3 - 1;
                     const float sx = q.x - (float)dx * edge_f, sy = q.y - (float)dy * edge_f, sz = q.z - (float)dz * edge_f;
-                    const double* qd = meanA + 3 * (base + o);
+                    const double* qd = meanA + 3 * (size_t)S.row[o];
                     const double* c = meanB + 3 * (size_t)rc.x;
                     const float4* cl = locB + (size_t)rc.x;
                     float blf = bl < 1e30 ? (float)bl * 1.00002f : 3.0e38f;
@@ -325,7 +420,7 @@ __global__ void __launch_bounds__(256) k_nn_sqdist_pairs(const Brick* __restrict
         while (need) {
             const int src = __ffs(need) - 1;
             need &= need - 1;
-            const int64_t rq = base + src;
+            const int64_t rq = S.row[src];
             const double qx = meanA[3 * rq], qy = meanA[3 * rq + 1], qz = meanA[3 * rq + 2];
             const uint64_t key = A[__shfl_sync(0xFFFFFFFFu, a, src)].key;
             const int bz = (int)key_z(key), by = (int)key_y(key), bx = (int)key_x(key);
@@ -359,19 +454,10 @@ __global__ void __launch_bounds__(256) k_nn_sqdist_pairs(const Brick* __restrict
             }
             if (lane == src) best = bq;
         }
-        if (valid) local_sum += best;
+        if (valid) nn2[r] = best;
     }
-    #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) local_sum += __shfl_xor_sync(0xFFFFFFFFu, local_sum, d);
     fb = __reduce_add_sync(0xFFFFFFFFu, fb);
-    if (lane == 0) s_red[w] = local_sum;
     if (lane == 0 && fb) atomicAdd(n_fallback, (unsigned long long)fb);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int i = 0; i < 8; ++i) t += s_red[i];
-        atomicAdd(acc, t);
-    }
 }
 
 struct VoxelMeans {
@@ -386,20 +472,24 @@ static void voxel_means(Ctx& cx, const float* d_P, int64_t n, const double mn[3]
     cudaStream_t st = cx.st;
     { Trace tr(cx, " cd grid_build"); grid_build(cx, d_P, n, mn, voxel, vm.gm); }
     Trace tr2(cx, " cd accumulate");
+    SQSM_CHECK(voxel <= 0.5, "Chamfer monitor: voxel_size above 0.5 m is not supported (fixed-point voxel sums)");
     int64_t rows = vm.gm.map.n_rows;
-    vm.mean.alloc(rows * 3, st);
-    vm.mean.zero();
+    DBuf<long long> sum(rows * 3, st);
+    sum.zero();
     DBuf<int32_t> cnt(rows, st);
     cnt.zero();
-    k_voxel_accumulate<<<div_up(n, 256), 256, 0, st>>>(d_P, vm.gm.pt_row.p, n, vm.mean.p, cnt.p);
-    k_voxel_mean<<<div_up(rows, 256), 256, 0, st>>>(vm.mean.p, cnt.p, rows);
+    k_voxel_accumulate<<<div_up(n, 256), 256, 0, st>>>(d_P, vm.gm.pt_row.p, vm.gm.ent_brick.p, vm.gm.ent_pos.p, vm.gm.map.bricks.p,
+                                                       vm.gm.g, n, sum.p, cnt.p);
+    vm.gm.ent_brick.release();
+    vm.gm.ent_pos.release();
     vm.row_brick.alloc(rows, st);
     vm.row_pos.alloc(rows, st);
     brickmap_expand_rows(cx, vm.gm.map, vm.row_brick.p, vm.row_pos.p);
+    vm.mean.alloc(rows * 3, st);
     vm.loc.alloc(rows, st);
-    k_local_means<<<div_up((int64_t)vm.gm.map.n_bricks * 32, 256), 256, 0, st>>>(vm.gm.map.bricks.p, vm.gm.map.n_bricks, vm.mean.p,
-                                                                                 vm.gm.g, vm.loc.p);
-    cx.launches += 3;
+    k_voxel_mean<<<div_up(rows, 256), 256, 0, st>>>(sum.p, cnt.p, vm.row_brick.p, vm.row_pos.p, vm.gm.map.bricks.p, vm.gm.g, rows,
+                                                    vm.mean.p, vm.loc.p);
+    cx.launches += 2;
 }
 
 // Partial Chamfer sums: the 1-NN squared distances of the voxel means of P to those of Q (sums[0]) and of Q to P
@@ -426,32 +516,84 @@ void chamfer_partial(Ctx& cx, const float* d_P, int64_t np, const float* d_Q, in
     for (int a = 0; a < 3; ++a) ext = std::max(ext, mx[a] - mn[a]);
     const double edge = 8.0 * voxel;
     int max_ring = (int)std::ceil(ext / edge) + 2;
-    DBuf<double> acc(2, st);
     DBuf<unsigned long long> nfb(2, st);
-    acc.zero();
     nfb.zero();
     const int nA = A.gm.map.n_bricks, nB = B.gm.map.n_bricks;
     DBuf<int2> abn((int64_t)nA * 32, st), ban((int64_t)nB * 32, st);
+    DBuf<int32_t> abid((int64_t)nA * 32, st), baid((int64_t)nB * 32, st);
     k_cross_neighbours<<<div_up((int64_t)nA * 32, 256), 256, 0, st>>>(A.gm.map.bricks.p, nA, B.gm.map.view(),
-                                                                      B.gm.map.bricks.p, abn.p);
+                                                                      B.gm.map.bricks.p, abn.p, abid.p);
     k_cross_neighbours<<<div_up((int64_t)nB * 32, 256), 256, 0, st>>>(B.gm.map.bricks.p, nB, A.gm.map.view(),
-                                                                      A.gm.map.bricks.p, ban.p);
-    const int64_t rA = A.gm.map.n_rows, rB = B.gm.map.n_rows;
-    int gA = (int)std::max<int64_t>(1, std::min<int64_t>(div_up(rA, 256), kNumSMs * 16));
-    int gB = (int)std::max<int64_t>(1, std::min<int64_t>(div_up(rB, 256), kNumSMs * 16));
-    k_nn_sqdist_pairs<<<gA, 256, 0, st>>>(A.gm.map.bricks.p, A.row_brick.p, rA, A.mean.p, A.loc.p, abn.p, B.gm.map.view(),
-                                        B.gm.map.bricks.p, B.mean.p, B.loc.p, A.gm.g, max_ring, shard, n_shards, acc.p, nfb.p);
-    k_nn_sqdist_pairs<<<gB, 256, 0, st>>>(B.gm.map.bricks.p, B.row_brick.p, rB, B.mean.p, B.loc.p, ban.p, A.gm.map.view(),
-                                        A.gm.map.bricks.p, A.mean.p, A.loc.p, A.gm.g, max_ring, shard, n_shards, acc.p + 1,
-                                        nfb.p + 1);
-    cx.launches += 4;
+                                                                      A.gm.map.bricks.p, ban.p, baid.p);
+    cx.launches += 2;
+    // cell-ring stages (SQSM_CD_RINGS, default "2,3": cubes of 5^3 then 7^3 voxel cells), then the brick-level search for
+    // whatever is still unsettled; "0" = brick-level search only
+    static const std::vector<int> rings = [] {
+        std::vector<int> r;
+        const char* e = getenv("SQSM_CD_RINGS");
+        std::string t = e ? e : "2,3";
+        for (size_t i = 0; i < t.size(); ++i)
+            if (t[i] >= '1' && t[i] <= '4' && r.size() < 4) r.push_back(t[i] - '0');
+        return r;
+    }();
+    int64_t n_left[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    auto direction = [&](VoxelMeans& X, VoxelMeans& Y, const int2* xyn, const int32_t* xyid, int which, double* h_sum) {
+        const int64_t rows = X.gm.map.n_rows;
+        DBuf<double> nn2(rows, st);
+        nn2.zero();                                              // rows of other shards contribute nothing
+        DBuf<int32_t> lst[2];
+        DBuf<int32_t> cnt(1, st);
+        const int32_t* cur = nullptr;                            // nullptr = all rows
+        int64_t n_cur = rows;
+        int flip = 0;
+        for (size_t s = 0; s < rings.size() && n_cur > 0; ++s) {
+            lst[flip].alloc(n_cur, st);
+            cnt.zero();
+            const int grid = div_up(n_cur, 256);
+#define SQSM_RING(R_)                                                                                                       \
+            k_nn_cells<R_><<<grid, 256, 0, st>>>(X.gm.map.bricks.p, X.row_brick.p, X.row_pos.p, cur, n_cur, X.mean.p, xyid,   \
+                                                 Y.gm.map.bricks.p, Y.mean.p, X.gm.g, shard, n_shards, nn2.p, lst[flip].p, cnt.p)
+            switch (rings[s]) {
+                case 1: SQSM_RING(1); break;
+                case 2: SQSM_RING(2); break;
+                case 3: SQSM_RING(3); break;
+                default: SQSM_RING(4); break;
+            }
+#undef SQSM_RING
+            cx.launches++;
+            int32_t h = 0;
+            SQSM_CUDA(cudaMemcpyAsync(&h, cnt.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            SQSM_CUDA(cudaStreamSynchronize(st));
+            cur = lst[flip].p;
+            n_cur = h;
+            n_left[which][s] = h;
+            flip ^= 1;
+        }
+        if (n_cur > 0) {
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(div_up(n_cur, 256), kNumSMs * 16));
+            k_nn_sqdist_pairs<<<grid, 256, 0, st>>>(X.gm.map.bricks.p, X.row_brick.p, cur, n_cur, X.mean.p, X.loc.p, xyn,
+                                                    Y.gm.map.view(), Y.gm.map.bricks.p, Y.mean.p, Y.loc.p, X.gm.g, max_ring, shard,
+                                                    n_shards, nn2.p, nfb.p + which);
+            cx.launches++;
+        }
+        // fixed-shape reduction over the rows in row order: the sum is bit-reproducible
+        DBuf<double> d_sum(1, st);
+        size_t tb = 0;
+        SQSM_CUDA(cub::DeviceReduce::Sum(nullptr, tb, nn2.p, d_sum.p, (int)rows, st));
+        DBuf<uint8_t> tmp((int64_t)tb + 16, st);
+        SQSM_CUDA(cub::DeviceReduce::Sum(tmp.p, tb, nn2.p, d_sum.p, (int)rows, st));
+        cx.launches += 2;
+        SQSM_CUDA(cudaMemcpyAsync(h_sum, d_sum.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+        SQSM_CUDA(cudaStreamSynchronize(st));
+    };
+    direction(A, B, abn.p, abid.p, 0, &sums[0]);
+    direction(B, A, ban.p, baid.p, 1, &sums[1]);
     if (Trace::enabled()) {
         auto f = nfb.to_host();
-        fprintf(stderr, "[trace]  cd nn: ring-search fallbacks %llu of %lld, %llu of %lld\n", f[0], (long long)A.gm.map.n_rows,
-                f[1], (long long)B.gm.map.n_rows);
+        fprintf(stderr, "[trace]  cd nn: unsettled after the cell rings %lld/%lld of %lld, %lld/%lld of %lld; brick-ring fallbacks %llu, %llu\n",
+                (long long)n_left[0][0], (long long)n_left[0][1], (long long)A.gm.map.n_rows, (long long)n_left[1][0],
+                (long long)n_left[1][1], (long long)B.gm.map.n_rows, f[0], f[1]);
     }
-    SQSM_CUDA(cudaMemcpyAsync(sums, acc.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    SQSM_CUDA(cudaStreamSynchronize(st));
     counts[0] = A.gm.map.n_rows;
     counts[1] = B.gm.map.n_rows;
 }

@@ -84,18 +84,27 @@ class ShardedTreeContraction:
     ``engine`` is a ``smartqsm_b200._lib.Engine`` (or any object with the same ``step_*`` methods) that already
     holds the full cloud (``set_points``) on ``device``.  Uses the default ``torch.distributed`` group (NCCL on
     GPUs, gloo on CPU tensors in the tests).
+
+    The exchange step is ONE all-gather per thunk: every rank contributes its segment (new points and accumulated
+    displacements, 24 B per point, padded to the longest segment) and receives everybody's; the concatenation in rank
+    order is the new cloud in canonical order.  On GPUs the collective is enqueued relative to the ENGINE's stream
+    (``torch.cuda.ExternalStream``), so there is no device-wide synchronisation between the network phase, the exchange
+    and the Chamfer phase - only the tiny host read of the segment sizes.
     """
 
     def __init__(self, engine, rank: int, world_size: int, device, monitored: bool) -> None:
         self.engine, self.rank, self.world, self.device, self.monitored = engine, rank, world_size, device, monitored
         self.history: List[Dict[str, Any]] = []
+        self.exchange_bytes = 0
+        self._stream = None
+        if getattr(device, "type", "cpu") == "cuda" and hasattr(engine, "stream_ptr"):
+            import torch
+            self._stream = torch.cuda.ExternalStream(engine.stream_ptr(), device=device)
 
-    def _sync(self) -> None:
-        # the engine works on its own CUDA stream: collectives issued on torch's stream must have completed
-        # before the engine reads their result (and vice versa the engine calls synchronise before returning)
+    def _ctx(self):
+        import contextlib
         import torch
-        if getattr(self.device, "type", "cpu") == "cuda":
-            torch.cuda.synchronize(self.device)
+        return torch.cuda.stream(self._stream) if self._stream is not None else contextlib.nullcontext()
 
     def contract(self) -> Dict[str, Any]:
         """One ``_contract`` thunk over all ranks; returns this rank's stats with the global decision."""
@@ -109,38 +118,43 @@ class ShardedTreeContraction:
         if st["skipped"]:
             self.history.append(st)
             return st
-        sizes_t = torch.zeros(self.world, dtype=torch.int64, device=self.device)
-        sizes_t[self.rank] = st["n_out"]
-        if self.world > 1:
-            dist.all_reduce(sizes_t)
-        sizes = [int(x) for x in sizes_t.tolist()]
-        offs = [0]
-        for s in sizes:
-            offs.append(offs[-1] + s)
-        total = offs[-1]
-        if total == 0:
-            raise RuntimeError("contraction produced no interior voxel")
-        new_p = torch.empty((total, 3), dtype=torch.float32, device=self.device)
-        new_d = torch.empty((total, 3), dtype=torch.float32, device=self.device)
-        lo, hi = offs[self.rank], offs[self.rank + 1]
-        if hi > lo:
-            eng.step_segment(new_p[lo:hi].data_ptr(), new_d[lo:hi].data_ptr())
-        if self.world > 1:
-            for r in range(self.world):                       # the exchange: every rank's segment to everybody
-                if sizes[r]:
-                    dist.broadcast(new_p[offs[r]:offs[r + 1]], src=r)
-                    dist.broadcast(new_d[offs[r]:offs[r + 1]], src=r)
-        self._sync()
-        t2 = time.perf_counter()
-        eng.step_set_candidate(new_p.data_ptr(), new_d.data_ptr(), total)
-        cd = float("nan")
-        if self.monitored:
-            sums, counts = eng.step_chamfer(self.rank, self.world)
-            t = torch.tensor(sums, dtype=torch.float64, device=self.device)
+        with self._ctx():
+            sizes_t = torch.zeros(self.world, dtype=torch.int64, device=self.device)
+            sizes_t[self.rank] = st["n_out"]
             if self.world > 1:
-                dist.all_reduce(t)
-            cd = float(t[0]) / counts[0] + float(t[1]) / counts[1]
-        st["accepted"] = int(eng.step_finish(self.monitored, cd))
+                dist.all_reduce(sizes_t)
+            sizes = [int(x) for x in sizes_t.tolist()]
+            total, longest = sum(sizes), max(sizes)
+            if total == 0:
+                raise RuntimeError("contraction produced no interior voxel")
+            # send[0] = points, send[1] = displacements of this rank's segment, padded to the longest segment
+            send = torch.empty((2, longest, 3), dtype=torch.float32, device=self.device)
+            if sizes[self.rank]:
+                eng.step_segment(send[0].data_ptr(), send[1].data_ptr())
+            if self.world > 1:
+                flat = torch.empty((self.world * 2, longest, 3), dtype=torch.float32, device=self.device)
+                dist.all_gather_into_tensor(flat, send)           # concatenation along dim 0 (gloo accepts only this form)
+                recv = flat.view(self.world, 2, longest, 3)
+                self.exchange_bytes = flat.numel() * 4
+                new_p = torch.cat([recv[r, 0, :sizes[r]] for r in range(self.world)])
+                new_d = torch.cat([recv[r, 1, :sizes[r]] for r in range(self.world)])
+            else:
+                new_p, new_d = send[0, :total].contiguous(), send[1, :total].contiguous()
+            if self._stream is None and getattr(self.device, "type", "cpu") == "cuda":
+                torch.cuda.synchronize(self.device)           # no shared stream: order by the host
+            t2 = time.perf_counter()
+            eng.step_set_candidate(new_p.data_ptr(), new_d.data_ptr(), total)
+            cd = float("nan")
+            if self.monitored:
+                sums, counts = eng.step_chamfer(self.rank, self.world)
+                t = torch.tensor(sums, dtype=torch.float64, device=self.device)
+                if self.world > 1:
+                    dist.all_reduce(t)
+                cd = float(t[0]) / counts[0] + float(t[1]) / counts[1]
+            st["accepted"] = int(eng.step_finish(self.monitored, cd))
+            if self._stream is not None:
+                new_p.record_stream(self._stream)
+                new_d.record_stream(self._stream)
         t3 = time.perf_counter()
         st["phase_s"] = {"begin": t1 - t0, "exchange": t2 - t1, "chamfer_finish": t3 - t2}
         st["chamfer"] = cd

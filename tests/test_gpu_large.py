@@ -1,0 +1,91 @@
+"""Parity at BASELINE-config sizes against fixtures the CPU oracle computed once (tests/golden/make_golden_large.py):
+one full iteration of C1 (1 M-point leaf-off tree) with every integer output compared through SHA-256 digests of a
+canonical form, and the whole 10-thunk stage on a 250 k-point tree.  ``-m gpu``."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+from tests.golden.make_golden_large import digest, level_digest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _state(which="leafoff"):
+    from oracle import weights
+    if weights.blob_path(which) is None:
+        pytest.skip("reference checkpoint blob not present (baseline/_ref)")
+    return weights.load_state(which, allow_random=False)
+
+
+def test_c1_iteration_against_oracle_fixture():
+    """C1 = BASELINE configs[0]: 1 000 000-point leaf-off tree, seed 1, leaf-off checkpoint, batch_size 16.  Integers
+    bit-exact (digests), floats within the split-mode tolerance on every 64th row and on the column sums."""
+    from smartqsm_b200._lib import Engine
+    from smartqsm_b200.synthetic import make_tree
+    path = os.path.join(GOLD, "c1_iteration.npz")
+    if not os.path.isfile(path):
+        pytest.skip("fixture not generated")
+    g = np.load(path)
+    pts = make_tree(1_000_000, 1)
+    eng = Engine(batch_size=16)
+    eng.load_state_dict(_state())
+    eng.debug_capture(True)
+    eng.set_points(pts)
+    st = eng.contract_step()
+    assert (st["n_in"], st["n_vox"], st["n_out"], st["n_cubes"], st["far_face_rows"]) == \
+        (int(g["n_in"]), int(g["n_vox"]), int(g["n_out"]), int(g["n_cubes"]), int(g["far_face_rows"]))
+    idx, win, mask = eng.debug_voxels()
+    assert digest(idx) == str(g["voxel_digest"]), "level-0 voxel coordinates / canonical order differ"
+    assert digest(win.astype(np.int64)) == str(g["winner_digest"]), "winning points differ"
+    assert digest(mask.astype(np.uint8)) == str(g["mask_digest"]), "interior masks differ"
+    shp, desc = eng.debug_batch_shapes(len(g["shapes"]))
+    assert np.array_equal(shp, g["shapes"])
+    n_levels = len(g["level_rows"])
+    assert np.array_equal(desc[:n_levels - 1], g["descended"])
+    for l in range(n_levels):
+        assert eng.debug_level_size(l) == int(g["level_rows"][l])
+        coords, nbr, parent, koff = eng.debug_level_tables(l, l + 1 < n_levels)
+        if parent is None:
+            parent = np.full(len(coords), -1, np.int32)
+            koff = (coords[:, 1] & 1) * 4 + (coords[:, 2] & 1) * 2 + (coords[:, 3] & 1)
+        assert level_digest(coords.astype(np.int64), nbr, parent, koff) == str(g["level_digests"][l]), f"rulebook of level {l} differs"
+    P, D = eng.result()
+    assert P.shape == (int(g["n_out"]), 3)
+    assert np.max(np.abs(P[::64].astype(np.float64) - g["P_sample"])) <= 4e-6          # metres, on coordinates of ~10 m
+    assert np.max(np.abs(D[::64] - g["D_sample"])) <= 6e-5 * float(g["D_absmax"])
+    assert np.max(np.abs(P.astype(np.float64).sum(0) - g["P_sum"])) <= 1e-6 * len(P)      # mean error per row below 1 um
+    assert np.max(np.abs(D.astype(np.float64).sum(0) - g["D_sum"])) <= 1e-6 * len(P)
+
+
+def test_full_stage_250k_against_oracle_fixture():
+    """10 thunks with the monitor on a 250 000-point tree: same accept / reject sequence, sizes within the sub-voxel flip
+    allowance, Chamfer values to 2e-5, final state and downstream counts close."""
+    from smartqsm_b200.core_algorithms import SpconvBasedContraction
+    from smartqsm_b200.synthetic import make_tree
+    path = os.path.join(GOLD, "run250k.npz")
+    if not os.path.isfile(path):
+        pytest.skip("fixture not generated")
+    g = np.load(path)
+    algo = SpconvBasedContraction(state_dict=_state(), batch_size=16, max_iteration=10, device="cuda",
+                                  monitored_by_chamfer_distance=True)
+    algo.input(points=make_tree(250_000, 6))
+    for f in algo.get_pipeline():
+        assert f() is None
+    acc = [int(h["accepted"]) for h in algo.history]
+    assert acc == [int(x) for x in g["accepted"]], "accept / reject sequence differs from the oracle"
+    for h, n_o, cd_o in zip(algo.history, g["n_out"], g["chamfer"]):
+        assert abs(h["n_out"] - int(n_o)) <= max(2, int(n_o) // 2000)                  # sub-voxel float flips only
+        assert abs(h["chamfer"] - cd_o) <= 2e-5 * cd_o or h["n_out"] != int(n_o)
+    out = algo.output()
+    P, D = out["contracted_points"], out["displacements"]
+    assert abs(len(P) - int(g["n_final"])) <= max(2, int(g["n_final"]) // 2000)
+    if len(P) == int(g["n_final"]):
+        assert np.max(np.abs(P[::16] - g["P_sample"])) <= 1e-4
+        assert np.max(np.abs(D[::16] - g["D_sample"])) <= 1e-4
+    ids, sk, rad = algo.produce_skeletal_points_and_radii(0.01)
+    assert abs(len(ids) - int(g["n_skeletal"])) <= max(2, int(g["n_skeletal"]) // 1000)
+    e = algo.radius_edges(0.055)
+    assert abs(len(e) - int(g["n_edges"])) <= max(20, int(g["n_edges"]) // 500)
