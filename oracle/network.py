@@ -145,8 +145,17 @@ class Weights:
         return self.t[k]
 
 
+BN_RECORDER: Optional[Dict[str, list]] = None   # set to {} to collect (sum, sum of squares, count) of every BatchNorm INPUT
+
+
 def _bn_relu(x: torch.Tensor, w: Weights, prefix: str, relu: bool = True) -> torch.Tensor:
     """``nn.BatchNorm1d(eps=1e-4)`` in eval mode + ``nn.ReLU`` (App. A)."""
+    if BN_RECORDER is not None:
+        xd = x.detach().double()
+        acc = BN_RECORDER.setdefault(prefix, [torch.zeros(x.shape[1], dtype=torch.float64), torch.zeros(x.shape[1], dtype=torch.float64), 0])
+        acc[0] += xd.sum(0)
+        acc[1] += (xd * xd).sum(0)
+        acc[2] += x.shape[0]
     y = F.batch_norm(x, w[prefix + ".running_mean"], w[prefix + ".running_var"],
                      w[prefix + ".weight"], w[prefix + ".bias"], False, 0.1, BN_EPS)
     return F.relu(y) if relu else y

@@ -29,11 +29,20 @@ from . import contraction as OC
 from . import network as ON
 from . import tiling as OT
 
-REFERENCE_ROOT = "/root/reference"
+def _reference_root() -> str:
+    """The reference checkout (authoring container) or its unmodified copy under ``baseline/_ref/SmartQSM``
+    (``oracle.weights.install_reference_python``; git-ignored, travels to the GPU box)."""
+    if os.path.isdir("/root/reference/external/SmartTreeXX"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "SmartQSM")
+
+
+REFERENCE_ROOT = _reference_root()
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "external", "SmartTreeXX"))
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "external", "SmartTreeXX", "models")) and \
+        os.path.isdir(os.path.join(REFERENCE_ROOT, "core"))
 
 
 # ------------------------------------------------------------------------------------ spconv.pytorch
@@ -228,7 +237,8 @@ def install() -> None:
     if _installed:
         return
     if not available():
-        raise RuntimeError("/root/reference is not present: the reference shim only works in the authoring container")
+        raise RuntimeError("neither /root/reference nor baseline/_ref/SmartQSM is present: the reference shim needs the "
+                           "reference's own Python (run __graft_entry__.build() in the authoring container)")
     sp = types.ModuleType("spconv")
     spp = types.ModuleType("spconv.pytorch")
     spu = types.ModuleType("spconv.pytorch.utils")

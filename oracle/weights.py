@@ -42,6 +42,35 @@ def export_reference_checkpoints(verbose: bool = False) -> None:
             print(f"exported {src} -> {dst}")
 
 
+REF_ROOT = "/root/reference"
+REF_INSTALL = os.path.join(BLOB_DIR, "SmartQSM")
+
+
+def install_reference_python(verbose: bool = False) -> None:
+    """The reference "install" of this tier: its pure-Python packages on the path (``core/``, ``utils/``,
+    ``external/SmartTreeXX/{datasets,models}``) copied UNMODIFIED under ``baseline/_ref/SmartQSM`` - git-ignored like the
+    checkpoints, so it never enters the history, but it travels to the GPU box, where ``/root/reference`` does not exist.
+    Used by ``oracle/refshim`` only (the boundary test drives the reference's own ``ThinningBasedSkeletonizationPipeline``
+    with the B200 plug-in registered, on a GPU).  Only where the reference checkout exists (this container)."""
+    import shutil
+    if not os.path.isdir(os.path.join(REF_ROOT, "core")):
+        return
+    for rel in ("core", "utils", os.path.join("external", "SmartTreeXX", "datasets"), os.path.join("external", "SmartTreeXX", "models")):
+        src, dst = os.path.join(REF_ROOT, rel), os.path.join(REF_INSTALL, rel)
+        if os.path.isdir(dst):
+            shutil.rmtree(dst)
+        shutil.copytree(src, dst, ignore=shutil.ignore_patterns("__pycache__", "*.pyc", "*.pth"))
+    for rel in (os.path.join("external", "__init__.py"), os.path.join("external", "SmartTreeXX", "__init__.py")):
+        src, dst = os.path.join(REF_ROOT, rel), os.path.join(REF_INSTALL, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        if os.path.isfile(src):
+            shutil.copyfile(src, dst)
+        elif not os.path.isfile(dst):
+            open(dst, "w").close()
+    if verbose:
+        print(f"installed the reference's Python packages under {REF_INSTALL}")
+
+
 def blob_path(which: str) -> Optional[str]:
     p = os.path.join(BLOB_DIR, NAMES[which] + ".npz")
     return p if os.path.isfile(p) else None

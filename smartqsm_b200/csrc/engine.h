@@ -83,11 +83,10 @@ constexpr int kTmZeroRows = 1024;        // rows of zeros behind every split-row
 
 struct Net;                             // conv.cu
 
-// Operands a tensor-core epilogue writes for ONE consumer of its output: FP16 hi / lo split of relu(out * alpha + beta)
+// Operands a tensor-core epilogue writes for ONE consumer of its output: FP16 hi | lo split of relu(out * alpha + beta)
 // (alpha == nullptr: of the raw output).  conv_tc.cu.
 struct TcFused {
-    void* hi = nullptr;
-    void* lo = nullptr;
+    void* hl = nullptr;                 // [n][hi C | lo C] interleaved __half rows
     const float* alpha = nullptr;
     const float* beta = nullptr;
 };

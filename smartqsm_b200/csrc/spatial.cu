@@ -526,12 +526,14 @@ void chamfer_partial(Ctx& cx, const float* d_P, int64_t np, const float* d_Q, in
     k_cross_neighbours<<<div_up((int64_t)nB * 32, 256), 256, 0, st>>>(B.gm.map.bricks.p, nB, A.gm.map.view(),
                                                                       A.gm.map.bricks.p, ban.p, baid.p);
     cx.launches += 2;
-    // cell-ring stages (SQSM_CD_RINGS, default "2,3": cubes of 5^3 then 7^3 voxel cells), then the brick-level search for
-    // whatever is still unsettled; "0" = brick-level search only
+    // optional cell-ring stages (SQSM_CD_RINGS, e.g. "2,3": cubes of 5^3 then 7^3 voxel cells) in front of the brick-level
+    // search, which then only sees what is still unsettled.  Default "0" = brick-level search only: on the C3 tree the ring
+    // stages settle 66 % / 41 % of the queries (P->Q / Q->P: the contracted cloud sits ~5 cm inside the old surface) but cost
+    // what they save (cd_nn 124 ms -> 125 ms with "2", 144 ms with "2,3"; profiles/r02_chamfer_notes.md)
     static const std::vector<int> rings = [] {
         std::vector<int> r;
         const char* e = getenv("SQSM_CD_RINGS");
-        std::string t = e ? e : "2,3";
+        std::string t = e ? e : "0";
         for (size_t i = 0; i < t.size(); ++i)
             if (t[i] >= '1' && t[i] <= '4' && r.size() < 4) r.push_back(t[i] - '0');
         return r;
