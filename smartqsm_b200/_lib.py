@@ -83,11 +83,12 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.isfile(LIB_PATH):
+    path = os.environ.get("SQSM_LIB") or LIB_PATH              # SQSM_LIB: A/B runs of an alternative build (tuning only)
+    if not os.path.isfile(path):
         raise RuntimeError(
-            f"{LIB_PATH} is missing: build it with `python -m smartqsm_b200.build` (nvcc, sm_100a). "
+            f"{path} is missing: build it with `python -m smartqsm_b200.build` (nvcc, sm_100a). "
             "smartqsm_b200 has no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, cp, i64, i32, f64 = C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, C.c_double
     P = C.POINTER
     sig = {

@@ -465,7 +465,8 @@ bool conv_tc(Ctx& cx, int ci, int co, int kv, bool cat, const float* inA, const 
              const uint8_t* sel_flag, float* out, int64_t n_out, bool precise, bool f16, const TcFused* fused = nullptr,
              int* range_flag = nullptr, const int32_t* up_parent = nullptr, const int32_t* up_koff = nullptr);
 void act_split(Ctx& cx, const float* in, const float* bn, int c, int bn_off, int bn_stride, int64_t n, float* hi, float* lo);
-void act_split_f16(Ctx& cx, const float* in, const float* bn, int c, int bn_off, int bn_stride, int64_t n, void* hl, int* range_flag);
+void act_split_f16(Ctx& cx, const float* in, const float* bn, int c, int bn_off, int bn_stride, int64_t n, void* hi, void* lo,
+                   int* range_flag);
 std::vector<float> make_tc_weight_image_f16(const float* w_kcico, int kv, int ci, int co);
 
 static bool conv_ffma(Ctx& cx, const ConvW& w, bool cat, const ConvArgs& a) {
@@ -491,7 +492,7 @@ static bool conv_ffma(Ctx& cx, const ConvW& w, bool cat, const ConvArgs& a) {
 // the consumer's BatchNorm + ReLU and writes the FP16 hi / lo operands itself (conv_tc.cu; bulk stores of whole tiles), so
 // the separate k_act_split_f16 pass and - when nothing else reads the tensor - its float32 round trip disappear.
 struct FusedSplit {
-    DBuf<float> hl;                      // [n][hi C | lo C] interleaved FP16 operand rows (2 * C halves = C floats per row)
+    DBuf<float> hi, lo;
     bool ready = false;
 };
 
@@ -555,28 +556,27 @@ static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, boo
         const bool precise = nw.mode == 1 || f16;
         const int ca = cat ? w.ci / 2 : w.ci;
         // FP16 operands take half the space of TF32 ones: allocate in float units either way
-        const int64_t elems = n_in * ca;
+        const int64_t elems = f16 ? (n_in * ca + 1) / 2 : n_in * ca;
         DBuf<float> a_hi, a_lo, b_hi, b_lo;
         const float *pa_hi = nullptr, *pa_lo = nullptr, *pb_hi = nullptr, *pb_lo = nullptr;
-        // FP16: interleaved operand rows [hi | lo] in ONE array per source (p?_lo unused); TF32: separate hi / lo arrays
         const bool preA = op.consume && op.consume->ready && f16;
         const bool preB = cat && op.consumeB && op.consumeB->ready && f16;
-        if (preA) pa_hi = op.consume->hl.p;
-        if (preB) pb_hi = op.consumeB->hl.p;
+        if (preA) { pa_hi = op.consume->hi.p; pa_lo = op.consume->lo.p; }
+        if (preB) { pb_hi = op.consumeB->hi.p; pb_lo = op.consumeB->lo.p; }
         if (!preA || (cat && !preB)) {
             ProfScope pa(cx, "act_split", (double)n_in * ca * ((preA ? 0 : 1) + (cat && !preB ? 1 : 0)) * (f16 ? 8.0 : 4.0 * (precise ? 3 : 2)), 0.0);
             if (!preA) {
-                a_hi.alloc(f16 ? n_in * ca : elems, cx.st);
-                if (precise && !f16) a_lo.alloc(elems, cx.st);
-                if (f16) act_split_f16(cx, inA, w.bn, ca, 0, w.ci, n_in, a_hi.p, nw.range_flag);
+                a_hi.alloc(elems, cx.st);
+                if (precise) a_lo.alloc(elems, cx.st);
+                if (f16) act_split_f16(cx, inA, w.bn, ca, 0, w.ci, n_in, a_hi.p, a_lo.p, nw.range_flag);
                 else act_split(cx, inA, w.bn, ca, 0, w.ci, n_in, a_hi.p, a_lo.p);
                 pa_hi = a_hi.p;
                 pa_lo = a_lo.p;
             }
             if (cat && !preB) {
-                b_hi.alloc(f16 ? n_in * ca : elems, cx.st);
-                if (precise && !f16) b_lo.alloc(elems, cx.st);
-                if (f16) act_split_f16(cx, inB, w.bn, ca, ca, w.ci, n_in, b_hi.p, nw.range_flag);
+                b_hi.alloc(elems, cx.st);
+                if (precise) b_lo.alloc(elems, cx.st);
+                if (f16) act_split_f16(cx, inB, w.bn, ca, ca, w.ci, n_in, b_hi.p, b_lo.p, nw.range_flag);
                 else act_split(cx, inB, w.bn, ca, ca, w.ci, n_in, b_hi.p, b_lo.p);
                 pb_hi = b_hi.p;
                 pb_lo = b_lo.p;
@@ -588,9 +588,11 @@ static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, boo
         if (f16 && nw.mode == 3) {
             for (int q = 0; q < 2; ++q) {
                 if (!op.produce[q]) continue;
-                op.produce[q]->hl.alloc(n_out * w.co, cx.st);             // 2 * co halves per row
+                const int64_t oe = (n_out * w.co + 1) / 2;
+                op.produce[q]->hi.alloc(oe, cx.st);
+                op.produce[q]->lo.alloc(oe, cx.st);
                 op.produce[q]->ready = true;
-                fused[q].hl = op.produce[q]->hl.p;
+                fused[q].hi = op.produce[q]->hi.p; fused[q].lo = op.produce[q]->lo.p;
                 fused[q].alpha = op.p_alpha[q]; fused[q].beta = op.p_beta[q];
                 any_fused = true;
             }

@@ -22,6 +22,12 @@
 //   * four epilogue warps tcgen05.ld the accumulator (two stages, so the next tile's MMAs overlap), sum the halves, add
 //     the residual, apply the "batch did not descend" select, store - and optionally write the consumer's operands.
 //
+// Measured and dropped in round 2 (profiles/r02_conv_knobs.md): interleaved [hi | lo] operand rows (fewer neighbouring rows per
+// 128-byte line: 127 -> 146 ms per C3 step for 16 -> 16), a "lean" gather loop in which every lane loads its own rulebook
+// entries instead of receiving them by shuffle (1.7 k instead of 8.8 k SASS instructions, but 8 more LSU requests per chunk
+// and warp: 127 -> 142 ms - the kernel is bound by the LSU / L2 request rate, not by issue slots), contiguous tile ranges per
+// CTA, cp.async.ca, shallower rings.
+//
 // The gather uses LDGSTS rather than TMA: conv_tma.cu is the same kernel on cp.async.bulk.tensor tile::gather4 and is
 // 10-25 % slower in the pipeline (profiles/r01_gather_microbench_notes.md); the weight chunk is small and L2 resident.
 #include "engine.h"
@@ -34,16 +40,17 @@ namespace sqsm {
 // ------------------------------------------------------------------------------------------ kernel
 
 struct TcSplitOut {            // fused activation split for one consumer of this output: hi/lo = split(act(out))
-    __half* hl;                // [n_out][hi CO | lo CO] interleaved operand rows, or nullptr
+    __half* hi;                // [n_out][CO] or nullptr
+    __half* lo;
     const float* alpha;        // [CO] scale / shift of the consumer's BatchNorm (+ ReLU); nullptr = raw values
     const float* beta;
 };
 
 struct TcArgs {
-    const float* inA;         // TF32 kernels: [n_in][CI] hi part of the activated input (first CI/2 channels when CAT);
-    const float* inB;         //   hi part of the second CI/2 channels when CAT; inA_lo / inB_lo: matching lo parts (PRECISE)
-    const float* inA_lo;      // FP16 kernels: inA / inB are INTERLEAVED rows [n_in][hi CS | lo CS] of __half (CS = channels of
-    const float* inB_lo;      //   the source), inA_lo / inB_lo are unused
+    const float* inA;         // [n_in][CI] TF32 hi part of the activated input (or first CI/2 channels when CAT)
+    const float* inB;         // hi part of the second CI/2 channels when CAT
+    const float* inA_lo;      // matching lo parts (PRECISE)
+    const float* inB_lo;
     const int32_t* nbr;       // [KV][n_out] or nullptr (identity, KV == 1)
     const int32_t* up_parent; // UP (inverse convolution): coarse row of every output row or -1, and its kernel offset;
     const int32_t* up_koff;   //   the rulebook entry (k, row) is parent[row] when koff[row] == k, absent otherwise
@@ -95,7 +102,7 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
     constexpr int B_BYTES = NP * 128;
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     constexpr bool BULK = tc_bulk(CO, F16, PRECISE);
-    constexpr int kTcStages = tc_stages(NP, tc_staging_bytes(CO, BULK));      // staging tiles sit behind the ring
+    constexpr int kTcStages = tc_stages(NP, tc_staging_bytes(CO, BULK));
     constexpr uint32_t FMT = F16 ? 0u : 2u;           // a/b format: F16 = 0, TF32 = 2 (UMMA::F16F32Format)
     constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     // PRECISE: the hi and lo weight tiles are adjacent in shared memory ([NP rows][128 B] each), so ONE instruction with
@@ -126,176 +133,93 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
-    // tiles of this CTA: strided over the grid.  (Measured and dropped: contiguous tile ranges per CTA, cp.async.ca with a
-    // shallower ring to leave room for L1 - no gain, the gather is not helped by L1 / L2 locality;
-    // profiles/r02_conv_knobs.md.  The ring depth must stay a compile-time constant: a run-time modulo in the producer and
-    // MMA loops cost 10-90 % of the kernel time.)
-    const int t_first = (int)blockIdx.x;
-    const int t_stride = (int)gridDim.x;
-    const int t_count = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (warp < kTcProdWarps) {
         // ===================== producers: rulebook rows -> cp.async gather into the swizzled smem tiles =====================
         // Nothing but rulebook entries passes through registers: the pre-split operands go global -> shared by LDGSTS and
         // the stage's mbarrier counts their arrival.
-        const int n_my_tiles = t_count;
+        const int n_my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
         const int total = n_my_tiles * NCH;               // chunk sequence of this CTA
         const int grp = warp >> 2;                        // producer group
         const int tp = t & (kTcProducers - 1);            // thread inside the group = tile row
         const int my_total = (total - grp + kTcGroups - 1) / kTcGroups;   // chunks grp, grp+G, ... of that sequence
-        if constexpr (F16 && PRECISE) {
-            // ---- FP16 kernels: LEAN gather loop.  The producer warps' own instruction stream was the limiter (about 500
-            // instructions per chunk: shuffles of rulebook entries, 64-bit address arithmetic per copy, ~1.6 us per chunk
-            // per group on every layer); the LSU itself sustains 8 cycles per LDGSTS (scripts/microbench/gather_map.cu).
-            // Now: everything that depends only on the lane is hoisted; lane l copies piece (l & 7) of tile rows
-            // (l >> 3) + 4m, m = 0..7, i.e. its kernel offset inside the chunk, its channel offset inside the INTERLEAVED
-            // source row [hi CS | lo CS] and its swizzle pattern are constants; rulebook entries are loaded directly by the
-            // lane that needs them (8 loads with immediate offsets, two chunks ahead), so there is no shuffle; a copy costs
-            // one max, one 64-bit multiply-add and two LDGSTS (hi tile, lo tile = +A_BYTES / + CS halves, immediates).
-            constexpr int CS = CAT ? CI / 2 : CI;             // channels per source row
-            constexpr int KPC = (CI >= CE) ? 1 : CE / CI;     // kernel offsets covered by one chunk
-            const int lane = tp & 31, piece = lane & 7, r0 = lane >> 3;
-            const int ci = (piece * PE) % CI, qlane = (piece * PE) / CI;
-            const bool second = CAT && ci >= CS;
-            const char* const srcbase = (const char*)(second ? a.inB : a.inA) + (size_t)(second ? ci - CS : ci) * 2;
-            const uint32_t row_off = (uint32_t)((tp & ~31) + r0) * 128u;
-            const uint32_t swz_even = row_off + (uint32_t)((piece ^ r0) << 4), swz_odd = row_off + (uint32_t)((piece ^ (r0 | 4)) << 4);
-            const uint32_t smem_base = smem_u32(smem);
-            int nb[3][8];
-            auto fetch_idx = [&](int i, int* n) {              // rulebook entries of the i-th chunk of this group, for THIS lane
-                const int c = grp + i * kTcGroups;
-                const int tile = t_first + (c / NCH) * t_stride;
-                const int j = c % NCH;
-                const int k = j * KPC + qlane;
-                const int row = tile * 128 + (tp & ~31) + r0;
-                const bool kvalid = (KT % CE == 0) || (j * CE + piece * PE < KT);
-                #pragma unroll
-                for (int m = 0; m < 8; ++m) {
-                    const int rm = row + 4 * m;
-                    int v = -1;
-                    if (kvalid && rm < a.n_out) {
-                        if (UP) {
-                            const int pr = __ldg(a.up_parent + rm);
-                            v = (pr >= 0 && __ldg(a.up_koff + rm) == k) ? pr : -1;
-                        } else v = a.nbr ? __ldg(a.nbr + (size_t)k * a.n_out + rm) : rm;
-                    }
-                    n[m] = v;
-                }
-            };
-            if (my_total > 0) fetch_idx(0, nb[0]);
-            if (my_total > 1) fetch_idx(1, nb[1]);
-            for (int i0 = 0; i0 < my_total; i0 += 3) {
-                #pragma unroll
-                for (int u = 0; u < 3; ++u) {
-                    const int i = i0 + u;
-                    if (i < my_total) {
-                        const int c = grp + i * kTcGroups;
-                        const uint32_t stage = (uint32_t)c % kTcStages, ph = ((uint32_t)c / kTcStages) & 1u;
-                        const int j = c % NCH;
-                        const uint32_t sA = smem_base + stage * STAGE_BYTES;
-                        const uint32_t sB = sA + 2 * A_BYTES;
-                        if (i + 2 < my_total) fetch_idx(i + 2, nb[(u + 2) % 3]);
-                        mbar_wait(empty0 + 8 * stage, ph ^ 1u);
-                        #pragma unroll
-                        for (int m = 0; m < 8; ++m) {
-                            const int n = nb[u][m];
-                            const char* src = srcbase + (size_t)(uint32_t)max(n, 0) * (size_t)(4 * CS);
-                            const uint32_t dst = sA + ((m & 1) ? swz_odd : swz_even) + (uint32_t)m * 512u;
-                            cp_async16(dst, src, n >= 0 ? 16u : 0u);
-                            cp_async16(dst + A_BYTES, src + CS * 2, n >= 0 ? 16u : 0u);
-                        }
-                        {   // weight chunk: hi tile then lo tile, already swizzled images (L2 resident)
-                            const float* wsrc = a.wimg + (size_t)j * (2 * B_BYTES / 4);
-                            constexpr int NPIECE = 2 * B_BYTES / 16;
-                            #pragma unroll
-                            for (int w = 0; w < (NPIECE + kTcProducers - 1) / kTcProducers; ++w) {
-                                const int q = tp + w * kTcProducers;
-                                if (q < NPIECE) cp_async16(sB + 16u * q, wsrc + 4 * q, 16u);
-                            }
-                        }
-                        cp_async_arrive(full0 + 8 * stage);   // one of the 128 arrivals, fires when this thread's copies landed
-                    }
-                }
-            }
-        } else {
-            // Lane l of a warp copies piece (l & 7) of tile rows (l >> 3) + 4m, m = 0..7: the eight lanes of a row
-            // move one contiguous 128 B (or 2 x 64 B) span.  Rulebook entries are loaded by the lane that owns the
-            // row, RI-1 chunks ahead (the only register loads left), and travel by shuffle.
-            constexpr int KPC = (CI >= CE) ? 1 : CE / CI;    // kernel offsets covered by one chunk
-            constexpr int RI = 8;
-            const int lane = tp & 31;
-            const int piece = lane & 7;
-            const uint32_t smem_base = smem_u32(smem);
-            int ibuf[RI][KPC];
-            auto issue_idx = [&](int i, int* nb) {            // i-th chunk of this group
-                const int c = grp + i * kTcGroups;
-                const int tile = t_first + (c / NCH) * t_stride;
-                const int j = c % NCH;
-                const int row = tile * 128 + tp;
-                #pragma unroll
-                for (int q = 0; q < KPC; ++q) {
-                    const int k = (j * CE) / CI + q;
-                    int n = -1;
-                    if (UP) {
-                        if (row < a.n_out && k < KV) {
-                            const int pr = __ldg(a.up_parent + row);
-                            if (pr >= 0 && __ldg(a.up_koff + row) == k) n = pr;
-                        }
-                    } else if (row < a.n_out && k < KV) n = a.nbr ? __ldg(a.nbr + (size_t)k * a.n_out + row) : row;
-                    nb[q] = n;
-                }
-            };
+        // Lane l of a warp copies piece (l & 7) of tile rows (l >> 3) + 4m, m = 0..7: the eight lanes of a row
+        // move one contiguous 128 B (or 2 x 64 B) span.  Rulebook entries are loaded by the lane that owns the
+        // row, RI-1 chunks ahead (the only register loads left), and travel by shuffle.
+        constexpr int KPC = (CI >= CE) ? 1 : CE / CI;    // kernel offsets covered by one chunk
+        constexpr int RI = 8;
+        const int lane = tp & 31;
+        const int piece = lane & 7;
+        const uint32_t smem_base = smem_u32(smem);
+        int ibuf[RI][KPC];
+        auto issue_idx = [&](int i, int* nb) {            // i-th chunk of this group
+            const int c = grp + i * kTcGroups;
+            const int tile = (int)blockIdx.x + (c / NCH) * (int)gridDim.x;
+            const int j = c % NCH;
+            const int row = tile * 128 + tp;
             #pragma unroll
-            for (int d = 0; d < RI - 1; ++d)
-                if (d < my_total) issue_idx(d, ibuf[d]);
-            for (int i0 = 0; i0 < my_total; i0 += RI) {
-                #pragma unroll
-                for (int u = 0; u < RI; ++u) {
-                    const int i = i0 + u;
-                    if (i < my_total) {
-                        const int c = grp + i * kTcGroups;
-                        const uint32_t stage = (uint32_t)c % kTcStages, ph = ((uint32_t)c / kTcStages) & 1u;
-                        const int j = c % NCH;
-                        const uint32_t sA_hi = smem_base + stage * STAGE_BYTES;
-                        const uint32_t sA_lo = sA_hi + A_BYTES;
-                        const uint32_t sB = sA_lo + A_BYTES;
-                        const int idx = j * CE + piece * PE;
-                        const int ci = idx % CI;
-                        mbar_wait(empty0 + 8 * stage, ph ^ 1u);
-                        #pragma unroll
-                        for (int m = 0; m < 8; ++m) {
-                            const int rl = (lane >> 3) + 4 * m;              // row inside this warp's 32 rows
-                            int n = -1;
-                            #pragma unroll
-                            for (int q = 0; q < KPC; ++q) {
-                                const int nq = __shfl_sync(0xFFFFFFFFu, ibuf[u][q], rl);
-                                if (KPC == 1 || (piece * PE) / CI == q) n = nq;
-                            }
-                            const bool on = (n >= 0) && (idx < KT);
-                            const size_t nn = on ? (size_t)n : 0;
-                            size_t eoff;
-                            bool second = false;
-                            if (CAT) { second = ci >= CI / 2; eoff = nn * (CI / 2) + (second ? ci - CI / 2 : ci); }
-                            else eoff = nn * CI + ci;
-                            const uint32_t rt = (uint32_t)(tp & ~31) + (uint32_t)rl;
-                            const uint32_t off = rt * 128u + (uint32_t)((piece ^ (int)(rt & 7u)) << 4);
-                            const uint32_t sz = on ? 16u : 0u;
-                            // element offsets are in operand elements (float)
-                            cp_async16(sA_hi + off, (const char*)(second ? a.inB : a.inA) + eoff * ES, sz);
-                            if (PRECISE) cp_async16(sA_lo + off, (const char*)(second ? a.inB_lo : a.inA_lo) + eoff * ES, sz);
-                        }
-                        {   // weight chunk: hi tile then lo tile, already swizzled images (L2 resident)
-                            const float* src = a.wimg + (size_t)j * (2 * B_BYTES / 4);
-                            constexpr int NPIECE = (PRECISE ? 2 : 1) * B_BYTES / 16;
-                            #pragma unroll
-                            for (int w = 0; w < (NPIECE + kTcProducers - 1) / kTcProducers; ++w) {
-                                int q = tp + w * kTcProducers;
-                                if (q < NPIECE) cp_async16(sB + 16u * q, src + 4 * q, 16u);
-                            }
-                        }
-                        cp_async_arrive(full0 + 8 * stage);   // one of the 128 arrivals, fires when this thread's copies landed
-                        if (i + RI - 1 < my_total) issue_idx(i + RI - 1, ibuf[(u + RI - 1) % RI]);
+            for (int q = 0; q < KPC; ++q) {
+                const int k = (j * CE) / CI + q;
+                int n = -1;
+                if (UP) {
+                    if (row < a.n_out && k < KV) {
+                        const int pr = __ldg(a.up_parent + row);
+                        if (pr >= 0 && __ldg(a.up_koff + row) == k) n = pr;
                     }
+                } else if (row < a.n_out && k < KV) n = a.nbr ? __ldg(a.nbr + (size_t)k * a.n_out + row) : row;
+                nb[q] = n;
+            }
+        };
+        #pragma unroll
+        for (int d = 0; d < RI - 1; ++d)
+            if (d < my_total) issue_idx(d, ibuf[d]);
+        for (int i0 = 0; i0 < my_total; i0 += RI) {
+            #pragma unroll
+            for (int u = 0; u < RI; ++u) {
+                const int i = i0 + u;
+                if (i < my_total) {
+                    const int c = grp + i * kTcGroups;
+                    const uint32_t stage = (uint32_t)c % kTcStages, ph = ((uint32_t)c / kTcStages) & 1u;
+                    const int j = c % NCH;
+                    const uint32_t sA_hi = smem_base + stage * STAGE_BYTES;
+                    const uint32_t sA_lo = sA_hi + A_BYTES;
+                    const uint32_t sB = sA_lo + A_BYTES;
+                    const int idx = j * CE + piece * PE;
+                    const int ci = idx % CI;
+                    mbar_wait(empty0 + 8 * stage, ph ^ 1u);
+                    #pragma unroll
+                    for (int m = 0; m < 8; ++m) {
+                        const int rl = (lane >> 3) + 4 * m;              // row inside this warp's 32 rows
+                        int n = -1;
+                        #pragma unroll
+                        for (int q = 0; q < KPC; ++q) {
+                            const int nq = __shfl_sync(0xFFFFFFFFu, ibuf[u][q], rl);
+                            if (KPC == 1 || (piece * PE) / CI == q) n = nq;
+                        }
+                        const bool on = (n >= 0) && (idx < KT);
+                        const size_t nn = on ? (size_t)n : 0;
+                        size_t eoff;
+                        bool second = false;
+                        if (CAT) { second = ci >= CI / 2; eoff = nn * (CI / 2) + (second ? ci - CI / 2 : ci); }
+                        else eoff = nn * CI + ci;
+                        const uint32_t rt = (uint32_t)(tp & ~31) + (uint32_t)rl;
+                        const uint32_t off = rt * 128u + (uint32_t)((piece ^ (int)(rt & 7u)) << 4);
+                        const uint32_t sz = on ? 16u : 0u;
+                        // element offsets are in operand elements (float or __half)
+                        cp_async16(sA_hi + off, (const char*)(second ? a.inB : a.inA) + eoff * ES, sz);
+                        if (PRECISE) cp_async16(sA_lo + off, (const char*)(second ? a.inB_lo : a.inA_lo) + eoff * ES, sz);
+                    }
+                    {   // weight chunk: hi tile then lo tile, already swizzled images (L2 resident)
+                        const float* src = a.wimg + (size_t)j * (2 * B_BYTES / 4);
+                        constexpr int NPIECE = (PRECISE ? 2 : 1) * B_BYTES / 16;
+                        #pragma unroll
+                        for (int w = 0; w < (NPIECE + kTcProducers - 1) / kTcProducers; ++w) {
+                            int q = tp + w * kTcProducers;
+                            if (q < NPIECE) cp_async16(sB + 16u * q, src + 4 * q, 16u);
+                        }
+                    }
+                    cp_async_arrive(full0 + 8 * stage);   // one of the 128 arrivals, fires when this thread's copies landed
+                    if (i + RI - 1 < my_total) issue_idx(i + RI - 1, ibuf[(u + RI - 1) % RI]);
                 }
             }
         }
@@ -305,11 +229,10 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
         // staging tiles of the bulk epilogue, behind the stage ring (row-major like global memory: one bulk copy per tile)
         float* const out_s = reinterpret_cast<float*>(smem + (size_t)kTcStages * STAGE_BYTES);
         float* const res_s = out_s + 128 * CO;
-        __half* const sp_s = reinterpret_cast<__half*>(res_s + 128 * CO);      // [2 splits][128][hi CO | lo CO]
+        __half* const sp_s = reinterpret_cast<__half*>(res_s + 128 * CO);      // [2 splits][hi, lo][128][CO]
         const uint32_t res_bar = smem_u32(&bars[2 * kTcMaxStages + 4]);
-        uint32_t res_it = 0;
-        for (uint32_t tile_it = 0; tile_it < (uint32_t)t_count; ++tile_it) {
-            const int tile = t_first + (int)tile_it * t_stride;
+        uint32_t tile_it = 0, res_it = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tile_it) {
             const uint32_t as = tile_it & 1u, aph = (tile_it >> 1) & 1u;
             const int row = tile * 128 + te;
             const bool live = row < a.n_out;
@@ -372,7 +295,7 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
                         if (F16) {
                             #pragma unroll
                             for (int q = 0; q < 2; ++q) {    // the consumers' BN + ReLU + FP16 hi/lo split, fused: 16-byte stores
-                                if (!a.sp[q].hl) continue;
+                                if (!a.sp[q].hi) continue;
                                 float x[8];
                                 float mx = 0.f;
                                 #pragma unroll
@@ -390,10 +313,10 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
                                     hw[i] = *reinterpret_cast<const uint32_t*>(&h);
                                     lw[i] = *reinterpret_cast<const uint32_t*>(&l);
                                 }
-                                // interleaved operand rows [hi CO | lo CO]
-                                __half* hp = BULK ? sp_s + q * 256 * CO + te * 2 * CO + ch : a.sp[q].hl + 2 * o + ch;
+                                __half* hp = BULK ? sp_s + (2 * q) * 128 * CO + te * CO + ch : a.sp[q].hi + o + ch;
+                                __half* lp = BULK ? sp_s + (2 * q + 1) * 128 * CO + te * CO + ch : a.sp[q].lo + o + ch;
                                 *reinterpret_cast<uint4*>(hp) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                                *reinterpret_cast<uint4*>(hp + CO) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                                *reinterpret_cast<uint4*>(lp) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                             }
                         }
                     }
@@ -407,7 +330,10 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
                     if (a.out) bulk_s2g(a.out + t0, smem_u32(out_s), rows_valid * CO * 4u);
                     #pragma unroll
                     for (int q = 0; q < 2; ++q)
-                        if (a.sp[q].hl) bulk_s2g(a.sp[q].hl + 2 * t0, smem_u32(sp_s + q * 256 * CO), rows_valid * CO * 4u);
+                        if (a.sp[q].hi) {
+                            bulk_s2g(a.sp[q].hi + t0, smem_u32(sp_s + (2 * q) * 128 * CO), rows_valid * CO * 2u);
+                            bulk_s2g(a.sp[q].lo + t0, smem_u32(sp_s + (2 * q + 1) * 128 * CO), rows_valid * CO * 2u);
+                        }
                     bulk_commit();
                 }
             }
@@ -415,8 +341,8 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
         if (BULK && te == 0) bulk_wait_all();               // stores complete before the shared memory goes away
     } else if ((t & 31) == 0) {
         // ===================== MMA issuer: one thread =====================
-        uint32_t it = 0;
-        for (uint32_t tile_it = 0; tile_it < (uint32_t)t_count; ++tile_it) {
+        uint32_t it = 0, tile_it = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tile_it) {
             const uint32_t as = tile_it & 1u, aph = (tile_it >> 1) & 1u;
             mbar_wait(tempty0 + 8 * as, aph ^ 1u);      // epilogue has drained this accumulator stage
             tc_fence_after();
@@ -473,20 +399,16 @@ __global__ void __launch_bounds__(256) k_act_split(const float4* __restrict__ in
     if (lo) lo[i] = make_float4(tf32_rn(x.x - h.x), tf32_rn(x.y - h.y), tf32_rn(x.z - h.z), tf32_rn(x.w - h.w));
 }
 
-// FP16 variant of the split: hi = fp16(x), lo = fp16(x - hi), written as INTERLEAVED operand rows [hi c | lo c] (the layout the
-// gather of k_conv_tc reads).  |x| must stay inside the FP16 range; a value above 3e4 raises the flag that the engine turns
-// into an error (measured activations of the checkpoints: <= ~1e3).
+// FP16 variant of the split: hi = fp16(x), lo = fp16(x - hi).  |x| must stay inside the FP16 range; a value above
+// 3e4 raises the flag that the engine turns into an error (measured activations of the checkpoints: <= ~1e3).
 __global__ void __launch_bounds__(256) k_act_split_f16(const float4* __restrict__ in, const float* __restrict__ bn, int c, int bn_off,
-                                                       int bn_stride, int64_t n4, uint2* __restrict__ out,
+                                                       int bn_stride, int64_t n4, uint2* __restrict__ hi, uint2* __restrict__ lo,
                                                        int* __restrict__ range_flag) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     float4 x = in[i];
-    const int c4 = c >> 2;
-    const int64_t row = i / c4;
-    const int q = (int)(i - row * c4);                    // group of 4 channels inside the row
     if (bn) {
-        const int ch = q * 4 + bn_off;
+        const int ch = (int)((i * 4) % c) + bn_off;
         x.x = fmaxf(fmaf(x.x, bn[ch + 0], bn[bn_stride + ch + 0]), 0.f);
         x.y = fmaxf(fmaf(x.y, bn[ch + 1], bn[bn_stride + ch + 1]), 0.f);
         x.z = fmaxf(fmaf(x.z, bn[ch + 2], bn[bn_stride + ch + 2]), 0.f);
@@ -495,16 +417,19 @@ __global__ void __launch_bounds__(256) k_act_split_f16(const float4* __restrict_
     if (!(fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))) < 3.0e4f)) *range_flag = 1;
     const __half2 h01 = __floats2half2_rn(x.x, x.y), h23 = __floats2half2_rn(x.z, x.w);
     const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-    const __half2 l01 = __floats2half2_rn(x.x - f01.x, x.y - f01.y), l23 = __floats2half2_rn(x.z - f23.x, x.w - f23.y);
-    uint2* o = out + row * (2 * c4) + q;                  // uint2 = 4 halves
-    o[0] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-    o[c4] = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+    hi[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    if (lo) {
+        const __half2 l01 = __floats2half2_rn(x.x - f01.x, x.y - f01.y), l23 = __floats2half2_rn(x.z - f23.x, x.w - f23.y);
+        lo[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+    }
 }
 
-void act_split_f16(Ctx& cx, const float* in, const float* bn, int c, int bn_off, int bn_stride, int64_t n, void* hl, int* range_flag) {
+void act_split_f16(Ctx& cx, const float* in, const float* bn, int c, int bn_off, int bn_stride, int64_t n, void* hi, void* lo,
+                   int* range_flag) {
     int64_t n4 = n * c / 4;
     if (n4 <= 0) return;
-    k_act_split_f16<<<div_up(n4, 256), 256, 0, cx.st>>>((const float4*)in, bn, c, bn_off, bn_stride, n4, (uint2*)hl, range_flag);
+    k_act_split_f16<<<div_up(n4, 256), 256, 0, cx.st>>>((const float4*)in, bn, c, bn_off, bn_stride, n4, (uint2*)hi, (uint2*)lo,
+                                                        range_flag);
     cx.launches++;
 }
 
@@ -576,15 +501,14 @@ static void launch_tc(Ctx& cx, const TcArgs& a0, bool precise, bool f16) {
     TcArgs a = a0;
     if (a.n_out <= 0) return;
     a.n_tiles = div_up(a.n_out, 128);
-
     constexpr int NP = CO < 16 ? 16 : CO;
     constexpr int STAGE = 2 * 128 * 128 + 2 * NP * 128;
     int grid = std::min(a.n_tiles, kNumSMs);
     if (f16) {
         constexpr int staging = tc_staging_bytes(CO, tc_bulk(CO, true, true));
         constexpr size_t smem = (size_t)tc_stages(NP, staging) * STAGE + staging + 1024;
-        // (the ring must hold at least as many stages as there are producer groups: with fewer, a group gets two ring
-        // cycles ahead of a stage's "empty" barrier and its parity wait is satisfied by the stale phase - a hang)
+        // the ring must hold at least as many stages as there are producer groups: with fewer, a group gets two ring cycles
+        // ahead of a stage's "empty" barrier and its parity wait is satisfied by the stale phase (a hang)
         static_assert(tc_stages(NP, staging) >= GR, "ring shallower than the number of producer groups");
         auto kern = k_conv_tc<CI, CO, KV, CAT, true, true, GR, UP>;
         SQSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -616,7 +540,8 @@ bool conv_tc(Ctx& cx, int ci, int co, int kv, bool cat, const float* inA, const 
              int* range_flag, const int32_t* up_parent, const int32_t* up_koff) {
     TcArgs a;
     for (int q = 0; q < 2; ++q) {
-        a.sp[q].hl = fused ? (__half*)fused[q].hl : nullptr;
+        a.sp[q].hi = fused ? (__half*)fused[q].hi : nullptr;
+        a.sp[q].lo = fused ? (__half*)fused[q].lo : nullptr;
         a.sp[q].alpha = fused ? fused[q].alpha : nullptr;
         a.sp[q].beta = fused ? fused[q].beta : nullptr;
     }

@@ -83,10 +83,11 @@ constexpr int kTmZeroRows = 1024;        // rows of zeros behind every split-row
 
 struct Net;                             // conv.cu
 
-// Operands a tensor-core epilogue writes for ONE consumer of its output: FP16 hi | lo split of relu(out * alpha + beta)
+// Operands a tensor-core epilogue writes for ONE consumer of its output: FP16 hi / lo split of relu(out * alpha + beta)
 // (alpha == nullptr: of the raw output).  conv_tc.cu.
 struct TcFused {
-    void* hl = nullptr;                 // [n][hi C | lo C] interleaved __half rows
+    void* hi = nullptr;
+    void* lo = nullptr;
     const float* alpha = nullptr;
     const float* beta = nullptr;
 };
