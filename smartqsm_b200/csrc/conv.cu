@@ -28,6 +28,8 @@ struct ConvArgs {
     const float* sel_src;    // [n_out][CO] value for rows with sel_flag == 0 (or nullptr)
     const uint8_t* sel_flag;
     float* out;              // [n_out][CO]
+    const uint8_t* tile_need;// per 128-row tile: 0 = no row of the tile can reach an interior output (decoder layers): the
+                             // block writes zeros instead of computing; nullptr = compute everything
     int n_out;
     int kc;                  // kernel offsets per shared-memory weight chunk
 };
@@ -49,6 +51,20 @@ __global__ void __launch_bounds__(256) k_conv(ConvArgs a) {
     const int t = threadIdx.x;
     const int slice = t / RG, rg = t % RG;
     const int row0 = blockIdx.x * TR + rg;
+    if (a.tile_need) {                                   // skipped block: defined (zero) outputs, no gather, no FMA
+        static_assert(TR % 128 == 0, "tile-need flags are per 128 rows");
+        bool any = false;
+        #pragma unroll
+        for (int q = 0; q < TR / 128; ++q) {
+            const int tile = blockIdx.x * (TR / 128) + q;
+            any |= (tile * 128 < a.n_out) && a.tile_need[tile] != 0;
+        }
+        if (!any) {
+            const int64_t e0 = (int64_t)blockIdx.x * TR * CO, e1 = min((int64_t)a.n_out * CO, e0 + (int64_t)TR * CO);
+            for (int64_t e = e0 + 4 * t; e < e1; e += 4 * 256) *reinterpret_cast<float4*>(a.out + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+            return;
+        }
+    }
     if (BN) {
         for (int i = t; i < 2 * CI; i += 256) sbn[i] = a.bn[i];
     }
@@ -271,6 +287,7 @@ __global__ void __launch_bounds__(256) k_heads(const float* __restrict__ feat, c
                                                float4* __restrict__ raw_out) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
+    if (!pred_out && !raw_out && out_pos[r] < 0) return;       // halo row: its prediction is discarded (:105-108)
     const HeadW& w = hp.w;
     const float* f = (sel_flag && sel_flag[r] == 0) ? sel_src + (size_t)r * 8 : feat + (size_t)r * 8;
     float4 f0 = *reinterpret_cast<const float4*>(f), f1 = *reinterpret_cast<const float4*>(f + 4);
@@ -463,7 +480,8 @@ static void conv_dispatch(Ctx& cx, const ConvArgs& a) {
 bool conv_tc(Ctx& cx, int ci, int co, int kv, bool cat, const float* inA, const float* inB, const float* inA_lo,
              const float* inB_lo, const int32_t* nbr, const float* wimg, const float* res, const float* sel_src,
              const uint8_t* sel_flag, float* out, int64_t n_out, bool precise, bool f16, const TcFused* fused = nullptr,
-             int* range_flag = nullptr, const int32_t* up_parent = nullptr, const int32_t* up_koff = nullptr);
+             int* range_flag = nullptr, const int32_t* up_parent = nullptr, const int32_t* up_koff = nullptr,
+             const int32_t* tile_list = nullptr, const int32_t* tile_count = nullptr);
 void act_split(Ctx& cx, const float* in, const float* bn, int c, int bn_off, int bn_stride, int64_t n, float* hi, float* lo);
 void act_split_f16(Ctx& cx, const float* in, const float* bn, int c, int bn_off, int bn_stride, int64_t n, void* hi, void* lo,
                    int* range_flag);
@@ -516,7 +534,33 @@ struct ConvOpts {
     bool need_fp32 = true;               // false: the float32 output has no reader (only with a fused split)
     const int32_t* up_parent = nullptr;  // inverse convolution (kv = 8): rulebook from the down-sample tables
     const int32_t* up_koff = nullptr;
+    const struct TileNeed* need = nullptr;   // decoder layers: only these tiles of 128 output rows are computed
 };
+
+// Which 128-row tiles of a level can influence an interior output (see need_tiles() below).
+struct TileNeed {
+    DBuf<uint8_t> flag;                  // [n_tiles] 1 = compute
+    DBuf<int32_t> list;                  // needed tile numbers, ascending
+    DBuf<int32_t> count;                 // [2]: needed tiles, skipped tiles
+    int n_tiles = 0;
+    bool valid = false;
+};
+
+// skipped tiles get defined contents: zeros (fp32 output and operand arrays alike)
+__global__ void __launch_bounds__(128) k_zero_tiles(const uint8_t* __restrict__ flag, int64_t n_rows, int co, float* __restrict__ out,
+                                                    uint2* __restrict__ h0, uint2* __restrict__ l0, uint2* __restrict__ h1,
+                                                    uint2* __restrict__ l1) {
+    if (flag[blockIdx.x]) return;
+    const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (row >= n_rows) return;
+    const int c4 = co / 4;
+    for (int q = 0; q < c4; ++q) {
+        const size_t e = (size_t)row * c4 + q;
+        if (out) reinterpret_cast<float4*>(out)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (h0) { h0[e] = make_uint2(0, 0); l0[e] = make_uint2(0, 0); }
+        if (h1) { h1[e] = make_uint2(0, 0); l1[e] = make_uint2(0, 0); }
+    }
+}
 
 static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, bool cat, const float* inA, const float* inB,
                      const int32_t* nbr, float* out, int64_t n_out, int64_t n_in, const ConvOpts& op = ConvOpts()) {
@@ -599,8 +643,15 @@ static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, boo
         }
         float* o_f32 = (any_fused && !op.need_fp32) ? nullptr : out;
         ProfScope ps(cx, fam, alg_bytes, 0.0);
+        const bool skip = op.need && op.need->valid && f16 && w.co <= 32;       // bulk-epilogue kernels only
+        if (skip) {
+            k_zero_tiles<<<op.need->n_tiles, 128, 0, cx.st>>>(op.need->flag.p, n_out, w.co, o_f32, (uint2*)fused[0].hi, (uint2*)fused[0].lo,
+                                                              (uint2*)fused[1].hi, (uint2*)fused[1].lo);
+            cx.launches++;
+        }
         if (conv_tc(cx, w.ci, w.co, w.kv, cat, pa_hi, pb_hi, pa_lo, pb_lo, nbr, f16 ? w.wimg16 : w.wimg, op.res, op.sel_src,
-                    op.sel_flag, o_f32, n_out, precise, f16, any_fused ? fused : nullptr, nw.range_flag, op.up_parent, op.up_koff))
+                    op.sel_flag, o_f32, n_out, precise, f16, any_fused ? fused : nullptr, nw.range_flag, op.up_parent, op.up_koff,
+                    skip ? op.need->list.p : nullptr, skip ? op.need->count.p : nullptr))
             return;
         for (int q = 0; q < 2; ++q) if (op.produce[q]) op.produce[q]->ready = false;
         if (up) throw CudaError("no tensor-core kernel for inverse convolution " + name);
@@ -609,6 +660,7 @@ static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, boo
     ConvArgs ar;
     ar.inA = inA; ar.inB = inB; ar.nbr = nbr; ar.w = w.w; ar.bn = w.bn; ar.res = op.res; ar.sel_src = op.sel_src;
     ar.sel_flag = op.sel_flag; ar.out = out; ar.n_out = (int)n_out; ar.kc = 0;
+    ar.tile_need = (op.need && op.need->valid) ? op.need->flag.p : nullptr;
     if (!conv_ffma(cx, w, cat, ar)) throw CudaError("no convolution kernel for layer " + name);
 }
 
@@ -624,6 +676,96 @@ static void keep_copy(Ctx& cx, ForwardBuffers& fb, const std::string& name, cons
     fb.keep_meta[name] = {level, ch};
 }
 
+// ---------------------------------------------------------------------------------- decoder tile skipping
+//
+// A cube sample carries a 0.4 m halo (40 voxels) whose rows only exist to give the interior rows their receptive field
+// (synthetic_tree.py:262-272); their own predictions are thrown away (spconv_based_contraction.py:104-108).  On the way DOWN
+// the halo is needed almost entirely (the receptive field of the U-Net is ~45 level-0 voxels), but on the way UP a row matters
+// only if an interior row can still see it: a 3^3 convolution at level l reaches one level-l voxel, an inverse convolution
+// reads the parent only.  With I = the per-axis interval of voxel coordinates that interior rows occupy (measured on the
+// rows of the pass, identical frame for every cube sample), the outputs of the decoder layers are needed inside
+//     level 0: I +- 2          level 1: (level 0 >> 1) +- 2          level 2: (level 1 >> 1) +- 2
+// (tail.b needs I, tail.a one voxel more, the inverse convolution and the skip operands one more; parents of a set [a, b]
+// are [a >> 1, b >> 1]).  Tiles of 128 rows (brick order: spatially compact) without any row inside the interval are not
+// computed - their outputs are zero-filled, so every tensor stays fully defined - which removes 20-40 % of the decoder
+// work.  The result is bit-identical: a computed row sees exactly the inputs it saw before (tests/test_gpu_parity.py).
+
+__global__ void __launch_bounds__(256) k_interior_bounds(const Brick* __restrict__ bricks, const int32_t* __restrict__ row_brick,
+                                                         const uint16_t* __restrict__ row_pos, const uint8_t* __restrict__ interior,
+                                                         int64_t n, int32_t* __restrict__ bounds) {
+    // grid-stride: a few thousand atomics in total (one set per block), not one set per warp on the same six addresses
+    __shared__ int s_lo[8][3], s_hi[8][3];
+    int lo[3] = {1 << 30, 1 << 30, 1 << 30}, hi[3] = {-1, -1, -1};
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        if (!interior[r]) continue;
+        const uint64_t key = bricks[row_brick[r]].key;
+        const uint32_t pos = row_pos[r];
+        const int c[3] = {(int)key_z(key) * 8 + (int)(pos >> 6), (int)key_y(key) * 8 + (int)((pos >> 3) & 7), (int)key_x(key) * 8 + (int)(pos & 7)};
+        #pragma unroll
+        for (int a = 0; a < 3; ++a) { lo[a] = min(lo[a], c[a]); hi[a] = max(hi[a], c[a]); }
+    }
+    const int w = threadIdx.x >> 5;
+    #pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = __reduce_min_sync(0xFFFFFFFFu, lo[a]);
+        hi[a] = __reduce_max_sync(0xFFFFFFFFu, hi[a]);
+        if ((threadIdx.x & 31) == 0) { s_lo[w][a] = lo[a]; s_hi[w][a] = hi[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int a = threadIdx.x;
+        int l = s_lo[0][a], h = s_hi[0][a];
+        for (int i = 1; i < 8; ++i) { l = min(l, s_lo[i][a]); h = max(h, s_hi[i][a]); }
+        if (h >= 0) { atomicMin(&bounds[a], l); atomicMax(&bounds[3 + a], h); }
+    }
+}
+
+// one block = one tile of 128 rows: flag = any row with all coordinates inside the level's interval
+__global__ void __launch_bounds__(128) k_tile_need(const Brick* __restrict__ bricks, const int32_t* __restrict__ row_brick,
+                                                   const uint16_t* __restrict__ row_pos, int64_t n, const int32_t* __restrict__ bounds,
+                                                   int level, uint8_t* __restrict__ flag, int32_t* __restrict__ flag32) {
+    const int64_t r = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    int lo[3], hi[3];
+    #pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = bounds[a] - 2;
+        hi[a] = bounds[3 + a] + 2;
+        for (int l = 0; l < level; ++l) { lo[a] = (lo[a] >> 1) - 2; hi[a] = (hi[a] >> 1) + 2; }
+    }
+    bool in = false;
+    if (r < n) {
+        const uint64_t key = bricks[row_brick[r]].key;
+        const uint32_t pos = row_pos[r];
+        const int c[3] = {(int)key_z(key) * 8 + (int)(pos >> 6), (int)key_y(key) * 8 + (int)((pos >> 3) & 7), (int)key_x(key) * 8 + (int)(pos & 7)};
+        in = c[0] >= lo[0] && c[0] <= hi[0] && c[1] >= lo[1] && c[1] <= hi[1] && c[2] >= lo[2] && c[2] <= hi[2];
+    }
+    const int any = __syncthreads_or(in ? 1 : 0);
+    if (threadIdx.x == 0) { flag[blockIdx.x] = any ? 1 : 0; flag32[blockIdx.x] = any ? 1 : 0; }
+}
+
+__global__ void __launch_bounds__(256) k_tile_list(const int32_t* __restrict__ flag32, const int32_t* __restrict__ scan, int n_tiles,
+                                                   int32_t* __restrict__ list, int32_t* __restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_tiles) return;
+    if (i == n_tiles) { count[0] = scan[n_tiles]; count[1] = n_tiles - scan[n_tiles]; return; }
+    if (flag32[i]) list[scan[i]] = i;
+}
+
+static void need_tiles(Ctx& cx, const LevelTables& L, int level, const int32_t* d_bounds, TileNeed& tn) {
+    cudaStream_t st = cx.st;
+    tn.n_tiles = div_up(L.n, 128);
+    tn.flag.alloc(tn.n_tiles, st);
+    tn.list.alloc(tn.n_tiles, st);
+    tn.count.alloc(2, st);
+    DBuf<int32_t> f32((int64_t)tn.n_tiles + 1, st), scan((int64_t)tn.n_tiles + 1, st);
+    SQSM_CUDA(cudaMemsetAsync(f32.p + tn.n_tiles, 0, sizeof(int32_t), st));
+    k_tile_need<<<tn.n_tiles, 128, 0, st>>>(L.map.bricks.p, L.row_brick.p, L.row_pos.p, L.n, d_bounds, level, tn.flag.p, f32.p);
+    exclusive_scan_i32(cx, f32.p, scan.p, (int64_t)tn.n_tiles + 1);
+    k_tile_list<<<div_up(tn.n_tiles + 1, 256), 256, 0, st>>>(f32.p, scan.p, tn.n_tiles, tn.list.p, tn.count.p);
+    cx.launches += 2;
+    tn.valid = true;
+}
+
 void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Rows& rows, int n_levels,
                  ForwardBuffers& fb, bool keep, float* d_newP, float* d_newD) {
     cudaStream_t st = cx.st;
@@ -636,6 +778,21 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
     FusedSplit sp_down[kLevels];             // enc[l] as operands of the down convolution of level l
     FusedSplit sp_skip[kLevels];             // enc[l] as operands (first half of the concat) of tail.a of level l
     FusedSplit sp_cur;                       // operands of the next inverse convolution, written by the producer of `cur`
+    // decoder tile skipping (not when activations are captured for the parity tests: those compare every row)
+    TileNeed need[kLevels];
+    const bool no_skip = getenv("SQSM_NO_TILE_SKIP") != nullptr;
+    if (!keep && !no_skip && n_levels > 1) {
+        ProfScope pn(cx, "need_tiles", (double)lv[0].n * 7.0, 0.0);
+        DBuf<int32_t> bounds(6, st);
+        static const int32_t init[6] = {1 << 30, 1 << 30, 1 << 30, -1, -1, -1};      // static: outlives the asynchronous copy
+        SQSM_CUDA(cudaMemcpyAsync(bounds.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        const int grid = (int)std::min<int64_t>(div_up(lv[0].n, 256), kNumSMs * 8);
+        k_interior_bounds<<<grid, 256, 0, st>>>(lv[0].map.bricks.p, lv[0].row_brick.p, lv[0].row_pos.p, rows.interior.p, lv[0].n,
+                                                bounds.p);
+        cx.launches++;
+        // levels 0 and 1 only: at level 2 the needed interval covers all but the outermost voxels (measured: no tile skipped)
+        for (int l = 0; l < n_levels - 1 && l < 2; ++l) need_tiles(cx, lv[l], l, bounds.p, need[l]);
+    }
     auto bn_a = [](const ConvW& w, int off) { return w.bn ? w.bn + off : nullptr; };
     auto bn_b = [](const ConvW& w, int off) { return w.bn ? w.bn + w.ci + off : nullptr; };
     // ---- encoder (smart_tree_xx.py:65-66, sparse_module.py:101-112)
@@ -722,6 +879,7 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
                 if (fuse && i_tc) { ou.produce[0] = &up_raw; }
                 if (fuse && a_tc) { ou.produce[1] = &up_act; ou.p_alpha[1] = bn_a(wa, c); ou.p_beta[1] = bn_b(wa, c); }
                 ou.need_fp32 = !(fuse && i_tc && a_tc);
+                ou.need = &need[l];
                 if (ou.need_fp32) up.alloc(n * c, st);
                 conv_any(cx, nw, L + ".up", false, cur.p, nullptr, nullptr, up.p, n, nc, ou);
             } else {
@@ -737,12 +895,14 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
                          2.0 * (double)lv[l].pairs * (2 * c * c + c * c) + 2.0 * (double)n * 2 * c * c);
             ConvOpts oi;
             oi.consumeB = &up_raw;
+            oi.need = &need[l];
             conv_any(cx, nw, L + ".tail.i", true, enc[l].p, up.p, nullptr, res.p, n, n, oi);
             up_raw = FusedSplit();
             FusedSplit sp_mid;
             ConvOpts oa;
             oa.consume = &sp_skip[l];
             oa.consumeB = &up_act;
+            oa.need = &need[l];
             if (fuse && tc_f16_layer(nw, wb)) { oa.produce[0] = &sp_mid; oa.p_alpha[0] = bn_a(wb, 0); oa.p_beta[0] = bn_b(wb, 0); oa.need_fp32 = false; }
             conv_any(cx, nw, L + ".tail.a", true, enc[l].p, up.p, lv[l].nbr.p, tmp[l].p, n, n, oa);
             sp_skip[l] = FusedSplit();
@@ -751,6 +911,7 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
             ConvOpts ob;
             ob.res = res.p; ob.sel_src = enc[l].p; ob.sel_flag = lv[l].row_desc.p;
             ob.consume = &sp_mid;
+            ob.need = &need[l];
             if (fuse && l > 0 && up_on_tc) {
                 const ConvW& wn = nw.conv.at("L" + std::to_string(l - 1) + ".up");
                 ob.produce[0] = &sp_cur; ob.p_alpha[0] = bn_a(wn, 0); ob.p_beta[0] = bn_b(wn, 0);

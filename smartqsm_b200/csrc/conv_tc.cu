@@ -61,6 +61,8 @@ struct TcArgs {
     float* out;               // [n_out][CO], or nullptr when only the fused splits below are wanted
     TcSplitOut sp[2];         // F16 kernels: operands of up to two consumers, written by the epilogue
     int* range_flag;
+    const int32_t* tile_list; // decoder tile skipping: the tiles to compute (ascending) and their number, or nullptr = all
+    const int32_t* tile_count;
     int n_out;
     int n_tiles;
 };
@@ -133,12 +135,13 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    const int n_tiles = a.tile_count ? __ldg(a.tile_count) : a.n_tiles;       // tiles this launch computes
 
     if (warp < kTcProdWarps) {
         // ===================== producers: rulebook rows -> cp.async gather into the swizzled smem tiles =====================
         // Nothing but rulebook entries passes through registers: the pre-split operands go global -> shared by LDGSTS and
         // the stage's mbarrier counts their arrival.
-        const int n_my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int n_my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
         const int total = n_my_tiles * NCH;               // chunk sequence of this CTA
         const int grp = warp >> 2;                        // producer group
         const int tp = t & (kTcProducers - 1);            // thread inside the group = tile row
@@ -154,7 +157,8 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
         int ibuf[RI][KPC];
         auto issue_idx = [&](int i, int* nb) {            // i-th chunk of this group
             const int c = grp + i * kTcGroups;
-            const int tile = (int)blockIdx.x + (c / NCH) * (int)gridDim.x;
+            const int tseq = (int)blockIdx.x + (c / NCH) * (int)gridDim.x;
+            const int tile = a.tile_list ? __ldg(a.tile_list + tseq) : tseq;
             const int j = c % NCH;
             const int row = tile * 128 + tp;
             #pragma unroll
@@ -232,7 +236,8 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
         __half* const sp_s = reinterpret_cast<__half*>(res_s + 128 * CO);      // [2 splits][hi, lo][128][CO]
         const uint32_t res_bar = smem_u32(&bars[2 * kTcMaxStages + 4]);
         uint32_t tile_it = 0, res_it = 0;
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tile_it) {
+        for (int tseq = blockIdx.x; tseq < n_tiles; tseq += gridDim.x, ++tile_it) {
+            const int tile = a.tile_list ? __ldg(a.tile_list + tseq) : tseq;
             const uint32_t as = tile_it & 1u, aph = (tile_it >> 1) & 1u;
             const int row = tile * 128 + te;
             const bool live = row < a.n_out;
@@ -342,7 +347,7 @@ __global__ void __launch_bounds__(tc_threads(GR), 1) k_conv_tc(const __grid_cons
     } else if ((t & 31) == 0) {
         // ===================== MMA issuer: one thread =====================
         uint32_t it = 0, tile_it = 0;
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tile_it) {
+        for (int tseq = blockIdx.x; tseq < n_tiles; tseq += gridDim.x, ++tile_it) {
             const uint32_t as = tile_it & 1u, aph = (tile_it >> 1) & 1u;
             mbar_wait(tempty0 + 8 * as, aph ^ 1u);      // epilogue has drained this accumulator stage
             tc_fence_after();
@@ -537,7 +542,8 @@ static void launch_tc(Ctx& cx, const TcArgs& a0, bool precise, bool f16) {
 bool conv_tc(Ctx& cx, int ci, int co, int kv, bool cat, const float* inA, const float* inB, const float* inA_lo,
              const float* inB_lo, const int32_t* nbr, const float* wimg, const float* res, const float* sel_src,
              const uint8_t* sel_flag, float* out, int64_t n_out, bool precise, bool f16, const TcFused* fused,
-             int* range_flag, const int32_t* up_parent, const int32_t* up_koff) {
+             int* range_flag, const int32_t* up_parent, const int32_t* up_koff, const int32_t* tile_list,
+             const int32_t* tile_count) {
     TcArgs a;
     for (int q = 0; q < 2; ++q) {
         a.sp[q].hi = fused ? (__half*)fused[q].hi : nullptr;
@@ -548,6 +554,7 @@ bool conv_tc(Ctx& cx, int ci, int co, int kv, bool cat, const float* inA, const 
     a.range_flag = range_flag;
     a.inA = inA; a.inB = inB; a.inA_lo = inA_lo; a.inB_lo = inB_lo; a.nbr = nbr; a.wimg = wimg; a.res = res; a.sel_src = sel_src; a.sel_flag = sel_flag;
     a.up_parent = up_parent; a.up_koff = up_koff;
+    a.tile_list = tile_list; a.tile_count = tile_count;
     a.out = out; a.n_out = (int)n_out; a.n_tiles = 0;
     const bool up = up_parent != nullptr;
 #define SQSM_TC_CASE(CI_, CO_, KV_, CAT_, UP_)                                    \

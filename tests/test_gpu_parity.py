@@ -573,3 +573,25 @@ def test_inverse_conv_paths_agree(leafoff_state, small_tree, monkeypatch):
     check_iteration(leafoff_state, small_tree)
     monkeypatch.setenv("SQSM_UPCONV_FFMA", "1")
     check_iteration(leafoff_state, small_tree)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_decoder_tile_skipping_is_bit_identical(leafoff_state, monkeypatch, mode):
+    """Halo tiles that no interior row can see are not computed in the decoder (conv.cu, need_tiles): the state after several
+    thunks, the Chamfer values and the decisions must not change by a single bit - in the tensor-core and the FFMA mode."""
+    from smartqsm_b200.synthetic import make_tree
+    pts = make_tree(300000, 33, True)
+    outs = []
+    for skip in (True, False):
+        if skip:
+            monkeypatch.delenv("SQSM_NO_TILE_SKIP", raising=False)
+        else:
+            monkeypatch.setenv("SQSM_NO_TILE_SKIP", "1")
+        eng = make_engine(leafoff_state, monitored_by_chamfer_distance=True, conv_mode=mode)
+        eng.set_points(pts)
+        stats = [eng.contract_step() for _ in range(4)]
+        P, D = eng.result()
+        outs.append((P, D, [(s["n_out"], s["accepted"], s["chamfer"]) for s in stats]))
+    monkeypatch.delenv("SQSM_NO_TILE_SKIP", raising=False)
+    assert outs[0][2] == outs[1][2]
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
