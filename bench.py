@@ -302,6 +302,19 @@ class ShardedJob:
         return stats, d2h, [sz]
 
 
+def result_digest(eng) -> dict:
+    """SHA-256 of the final state (contracted points, displacements), the skeletal sample ids and radii, and the edge
+    count: the sharded run (C5) must reproduce the single-GPU digest."""
+    import hashlib
+    P, D = eng.result()
+    ids, sk, rad = eng.skeletal_sample(SKELETAL_VOXEL)
+    e = eng.radius_graph(EDGE_R, fetch=False)
+    h = hashlib.sha256()
+    for a in (P, D, ids, rad):
+        h.update(np.ascontiguousarray(a).tobytes())
+    return {"sha256": h.hexdigest(), "n_final": int(len(P)), "skeletal_points": int(len(ids)), "edges": int(e)}
+
+
 _MONITORED = {}
 
 
@@ -444,6 +457,7 @@ def main_b200(args):
     # every later thunk would recompute the same rejection; reported beside the headline, never instead of it)
     eng_l = make_engine(True, True)
     latched_ms, (stats_l, _, sizes_l) = timed(eng_l, False)
+    digest = result_digest(eng_l) if (rank == 0 and args.workload == "C5") else None      # rank 0 holds the final state
     eng_l.close()
     if sizes_l != sizes:
         raise RuntimeError(f"latched run produced {sizes_l}, unlatched {sizes}: the latch must not change results")
@@ -545,6 +559,7 @@ def main_b200(args):
             line["config"]["trees"] = n_trees
             line["config"]["tree_sizes_min_max"] = [min(sizes_all), max(sizes_all)]
         if args.workload == "C5":
+            line["result_digest"] = digest
             line["exchange"] = {"collective": "all_gather_into_tensor (NCCL), once per thunk, on the engine's stream",
                                 "bytes_per_thunk_per_rank": job.exchange_bytes,
                                 "replicated_per_rank": "tiling, Chamfer voxel means; skeletal sampling + radius graph on rank 0 only"}
