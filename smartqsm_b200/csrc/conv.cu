@@ -269,6 +269,119 @@ static void launch_conv(Ctx& cx, ConvArgs a) {
     cx.launches++;
 }
 
+// Level-0 variant (C_out = 8, 27 offsets, 18-21 % of the neighbours exist): one thread per output row walks ONLY the row's
+// present offsets.  Phase 1 reads the 27 rulebook entries of the row (coalesced over the block) and compacts the present
+// ones into a per-thread column of shared memory plus a 27-bit mask; phase 2 loops over that list - a per-lane trip count
+// (mean 5, warp maximum about 10) instead of 27 warp-wide iterations of which 94-97 % cannot be skipped.  The price is a
+// per-lane kernel offset: the weight reads are no longer warp broadcasts.  The weight image of an offset is padded to an
+// odd number of 16-byte chunks (2*CI + 1), so lanes with different offsets fall into different bank groups and a
+// float4 weight read costs 2-3 wavefronts instead of 8-10.  Accumulation order per row = ascending offset, like k_conv.
+template <int CI, bool BN>
+__global__ void __launch_bounds__(256) k_conv_sp8(ConvArgs a) {
+    constexpr int CO = 8, KV = 27, WS = CI * CO + 4;       // padded floats per offset
+    extern __shared__ __align__(16) float smem[];
+    float* sbn = smem;                                   // [2][CI] (+ pad to 16 floats)
+    float* sw = smem + 16;                               // [27][WS]
+    int32_t* list = reinterpret_cast<int32_t*>(sw + KV * WS);   // [27][256] present neighbours of thread t, column t
+
+    const int t = threadIdx.x;
+    const int row = blockIdx.x * 256 + t;
+    if (a.tile_need) {
+        const int tile = blockIdx.x * 2;
+        const bool any = a.tile_need[tile] != 0 || ((tile + 1) * 128 < a.n_out && a.tile_need[tile + 1] != 0);
+        if (!any) {
+            const int64_t e0 = (int64_t)blockIdx.x * 256 * CO, e1 = min((int64_t)a.n_out * CO, e0 + (int64_t)256 * CO);
+            for (int64_t e = e0 + 4 * t; e < e1; e += 4 * 256) *reinterpret_cast<float4*>(a.out + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+            return;
+        }
+    }
+    if (BN) { if (t < 2 * CI) sbn[t] = a.bn[t]; }
+    for (int i = t; i < KV * CI * CO / 4; i += 256) {
+        const int k = i / (CI * CO / 4), r = i % (CI * CO / 4);
+        *reinterpret_cast<float4*>(sw + k * WS + 4 * r) = reinterpret_cast<const float4*>(a.w)[i];
+    }
+    unsigned mask = 0;
+    int cnt = 0;
+    if (row < a.n_out) {
+        #pragma unroll
+        for (int k = 0; k < KV; ++k) {
+            const int n = __ldg(a.nbr + (size_t)k * a.n_out + row);
+            if (n >= 0) { list[cnt * 256 + t] = n; mask |= 1u << k; ++cnt; }
+        }
+    }
+    __syncthreads();
+
+    float2 acc[CO / 2];
+    #pragma unroll
+    for (int c = 0; c < CO / 2; ++c) acc[c] = make_float2(0.0f, 0.0f);
+    float4 x[CI / 4], xn[CI / 4];
+    if (cnt > 0) {
+        const float4* p = reinterpret_cast<const float4*>(a.inA + (size_t)list[t] * CI);
+        #pragma unroll
+        for (int c = 0; c < CI / 4; ++c) xn[c] = __ldg(p + c);
+    }
+    for (int i = 0; i < cnt; ++i) {
+        #pragma unroll
+        for (int c = 0; c < CI / 4; ++c) x[c] = xn[c];
+        if (i + 1 < cnt) {                               // next neighbour's features in flight while this one is multiplied
+            const float4* p = reinterpret_cast<const float4*>(a.inA + (size_t)list[(i + 1) * 256 + t] * CI);
+            #pragma unroll
+            for (int c = 0; c < CI / 4; ++c) xn[c] = __ldg(p + c);
+        }
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float* wk = sw + k * WS;
+        #pragma unroll
+        for (int c0 = 0; c0 < CI; c0 += 4) {
+            float4 v = x[c0 / 4];
+            if (BN) {
+                v.x = fmaxf(fmaf(v.x, sbn[c0 + 0], sbn[CI + c0 + 0]), 0.0f);
+                v.y = fmaxf(fmaf(v.y, sbn[c0 + 1], sbn[CI + c0 + 1]), 0.0f);
+                v.z = fmaxf(fmaf(v.z, sbn[c0 + 2], sbn[CI + c0 + 2]), 0.0f);
+                v.w = fmaxf(fmaf(v.w, sbn[c0 + 3], sbn[CI + c0 + 3]), 0.0f);
+            }
+            #pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const float s = comp4(v, cc);
+                const float2 ss = make_float2(s, s);
+                const float4 w0 = *reinterpret_cast<const float4*>(wk + (c0 + cc) * CO);
+                const float4 w1 = *reinterpret_cast<const float4*>(wk + (c0 + cc) * CO + 4);
+                acc[0] = __ffma2_rn(ss, make_float2(w0.x, w0.y), acc[0]);
+                acc[1] = __ffma2_rn(ss, make_float2(w0.z, w0.w), acc[1]);
+                acc[2] = __ffma2_rn(ss, make_float2(w1.x, w1.y), acc[2]);
+                acc[3] = __ffma2_rn(ss, make_float2(w1.z, w1.w), acc[3]);
+            }
+        }
+    }
+    if (row >= a.n_out) return;
+    const size_t o = (size_t)row * CO;
+    const bool take_src = a.sel_flag && a.sel_flag[row] == 0;
+    #pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        float4 r = make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
+        if (a.res) {
+            const float4 e = *reinterpret_cast<const float4*>(a.res + o + 4 * q);
+            r.x += e.x; r.y += e.y; r.z += e.z; r.w += e.w;
+        }
+        if (take_src) r = *reinterpret_cast<const float4*>(a.sel_src + o + 4 * q);
+        *reinterpret_cast<float4*>(a.out + o + 4 * q) = r;
+    }
+}
+
+template <int CI, bool BN>
+static void launch_conv_sp8(Ctx& cx, const ConvArgs& a) {
+    if (a.n_out <= 0) return;
+    const size_t smem = (size_t)(16 + 27 * (CI * 8 + 4)) * 4 + (size_t)27 * 256 * 4;
+    auto kern = k_conv_sp8<CI, BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SQSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    kern<<<div_up(a.n_out, 256), 256, smem, cx.st>>>(a);
+    cx.launches++;
+}
+
 // ---------------------------------------------------------------------------------- heads + contraction
 
 struct HeadParams { HeadW w; };
@@ -489,6 +602,12 @@ std::vector<float> make_tc_weight_image_f16(const float* w_kcico, int kv, int ci
 
 static bool conv_ffma(Ctx& cx, const ConvW& w, bool cat, const ConvArgs& a) {
     const bool bn = w.bn != nullptr;
+    // level-0 SubM layers: per-row loop over the present offsets (SQSM_L0_DENSE=1 restores the dense 27-offset kernel)
+    const bool sparse_l0 = getenv("SQSM_L0_DENSE") == nullptr;
+    if (sparse_l0 && w.kv == 27 && w.co == 8 && !cat && a.nbr) {
+        if (w.ci == 8 && bn) { launch_conv_sp8<8, true>(cx, a); return true; }
+        if (w.ci == 4 && !bn) { launch_conv_sp8<4, false>(cx, a); return true; }
+    }
 #define SQSM_FF_CASE(CI_, CO_, KV_, BN_, CAT_)                                                    \
     if (w.ci == CI_ && w.co == CO_ && w.kv == KV_ && bn == BN_ && cat == CAT_) {                  \
         conv_dispatch<CI_, CO_, KV_, BN_, CAT_>(cx, a);                                           \

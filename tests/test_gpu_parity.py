@@ -595,3 +595,27 @@ def test_decoder_tile_skipping_is_bit_identical(leafoff_state, monkeypatch, mode
     monkeypatch.delenv("SQSM_NO_TILE_SKIP", raising=False)
     assert outs[0][2] == outs[1][2]
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_level0_sparse_loop_equals_dense_kernel(leafoff_state, small_tree, monkeypatch):
+    """Level-0 SubM layers: the kernel that walks only a row's present offsets (k_conv_sp8) accumulates in the same order
+    as the dense 27-offset kernel (absent neighbours add exact zeros there), so the states must be bit-identical; both
+    are within tolerance of the oracle (check_iteration)."""
+    from smartqsm_b200.synthetic import make_tree
+    check_iteration(leafoff_state, small_tree)
+    pts = make_tree(200000, 12, True)
+    outs = []
+    for dense in (False, True):
+        if dense:
+            monkeypatch.setenv("SQSM_L0_DENSE", "1")
+        else:
+            monkeypatch.delenv("SQSM_L0_DENSE", raising=False)
+        eng = make_engine(leafoff_state, monitored_by_chamfer_distance=True)
+        eng.set_points(pts)
+        stats = [eng.contract_step() for _ in range(3)]
+        P, D = eng.result()
+        outs.append((P, D, [(s["n_out"], s["accepted"], s["chamfer"]) for s in stats]))
+    check_iteration(leafoff_state, small_tree)           # dense kernel against the oracle as well
+    monkeypatch.delenv("SQSM_L0_DENSE", raising=False)
+    assert outs[0][2] == outs[1][2]
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
