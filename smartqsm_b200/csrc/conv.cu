@@ -13,6 +13,7 @@
 // the weights of the current offsets from shared memory as warp-broadcast float4 reads.  Residual
 // add, skip-concat (two input pointers) and the per-batch "did not descend" select are fused in.
 #include "engine.h"
+#include <cuda_fp16.h>
 #include <algorithm>
 #include <cstring>
 
@@ -269,71 +270,114 @@ static void launch_conv(Ctx& cx, ConvArgs a) {
     cx.launches++;
 }
 
-// Level-0 variant (C_out = 8, 27 offsets, 18-21 % of the neighbours exist): one thread per output row walks ONLY the row's
-// present offsets.  Phase 1 reads the 27 rulebook entries of the row (coalesced over the block) and compacts the present
-// ones into a per-thread column of shared memory plus a 27-bit mask; phase 2 loops over that list - a per-lane trip count
-// (mean 5, warp maximum about 10) instead of 27 warp-wide iterations of which 94-97 % cannot be skipped.  The price is a
-// per-lane kernel offset: the weight reads are no longer warp broadcasts.  The weight image of an offset is padded to an
-// odd number of 16-byte chunks (2*CI + 1), so lanes with different offsets fall into different bank groups and a
-// float4 weight read costs 2-3 wavefronts instead of 8-10.  Accumulation order per row = ascending offset, like k_conv.
-template <int CI, bool BN>
-__global__ void __launch_bounds__(256) k_conv_sp8(ConvArgs a) {
-    constexpr int CO = 8, KV = 27, WS = CI * CO + 4;       // padded floats per offset
+// Sparse-loop variant for the layers whose rulebook is mostly empty (level 0: 18-21 % of the 27 neighbours exist; k = 8 down
+// convolution out of level 0: 1.7 of 8 children; inverse convolutions: exactly one (parent, offset) pair per row).
+// One thread per output row walks ONLY the row's present offsets.  Phase 1 reads the KV rulebook entries of the row
+// (coalesced over the block) and compacts the present ones into a per-thread column of shared memory plus a bit mask;
+// phase 2 loops over that list - a per-lane trip count (level 0: mean 5, warp maximum about 10) instead of 27 warp-wide
+// iterations of which 94-97 % cannot be skipped.  The price is a per-lane kernel offset: the weight reads are no longer warp
+// broadcasts.  The weight image of an offset is padded to an ODD number of 16-byte chunks (CI*CO/4 + 1), so lanes with
+// different offsets fall into different bank groups and a float4 weight read costs 1-3 wavefronts instead of 8-10.
+// Accumulation order per row = ascending offset, channels inside an offset in order, like k_conv (absent neighbours add
+// exact zeros there): the two kernels are bit-identical.  The epilogue can also write the FP16 hi / lo operands of up to two
+// tensor-core consumers (same arithmetic as k_act_split_f16 / the conv_tc epilogue).
+struct SpOut { __half* hi; __half* lo; const float* alpha; const float* beta; };
+struct SpArgs {
+    ConvArgs c;
+    const int32_t* up_parent;    // UP: inverse convolution, the single pair of row r is (up_parent[r], up_koff[r])
+    const int32_t* up_koff;
+    SpOut sp[2];
+    int* range_flag;
+};
+
+template <int CI, int CO, int KV, bool BN, bool CAT, bool UP>
+__global__ void __launch_bounds__(256) k_conv_sp(SpArgs s) {
+    const ConvArgs& a = s.c;
+    constexpr int WS = CI * CO + 4;                      // padded floats per offset
+    constexpr bool PREF = !UP && CI <= 16;               // software prefetch of the next neighbour's features
+    constexpr int CA = CAT ? CI / 2 : CI;                // channels per source
     extern __shared__ __align__(16) float smem[];
-    float* sbn = smem;                                   // [2][CI] (+ pad to 16 floats)
-    float* sw = smem + 16;                               // [27][WS]
-    int32_t* list = reinterpret_cast<int32_t*>(sw + KV * WS);   // [27][256] present neighbours of thread t, column t
+    float* sbn = smem;                                   // [2][CI]
+    float* sw = smem + 2 * 64;                           // [KV][WS]
+    int32_t* list = reinterpret_cast<int32_t*>(sw + KV * WS);   // [LK][256] present neighbours of thread t, column t
 
     const int t = threadIdx.x;
-    const int row = blockIdx.x * 256 + t;
-    if (a.tile_need) {
-        const int tile = blockIdx.x * 2;
-        const bool any = a.tile_need[tile] != 0 || ((tile + 1) * 128 < a.n_out && a.tile_need[tile + 1] != 0);
-        if (!any) {
-            const int64_t e0 = (int64_t)blockIdx.x * 256 * CO, e1 = min((int64_t)a.n_out * CO, e0 + (int64_t)256 * CO);
-            for (int64_t e = e0 + 4 * t; e < e1; e += 4 * 256) *reinterpret_cast<float4*>(a.out + e) = make_float4(0.f, 0.f, 0.f, 0.f);
-            return;
-        }
-    }
+    // persistent blocks: the weight image is staged once per block, then the block walks 256-row groups
     if (BN) { if (t < 2 * CI) sbn[t] = a.bn[t]; }
     for (int i = t; i < KV * CI * CO / 4; i += 256) {
         const int k = i / (CI * CO / 4), r = i % (CI * CO / 4);
         *reinterpret_cast<float4*>(sw + k * WS + 4 * r) = reinterpret_cast<const float4*>(a.w)[i];
     }
+    __syncthreads();
+    const int n_groups = (a.n_out + 255) / 256;
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const int row = grp * 256 + t;
+    if (a.tile_need) {
+        const int tile = grp * 2;
+        const bool any = a.tile_need[tile] != 0 || ((tile + 1) * 128 < a.n_out && a.tile_need[tile + 1] != 0);
+        if (!any) {                                      // skipped group: defined (zero) outputs, no gather, no FMA
+            const int64_t e0 = (int64_t)grp * 256 * CO, e1 = min((int64_t)a.n_out * CO, e0 + (int64_t)256 * CO);
+            if (a.out)
+                for (int64_t e = e0 + 4 * t; e < e1; e += 4 * 256) *reinterpret_cast<float4*>(a.out + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+            #pragma unroll
+            for (int q = 0; q < 2; ++q)
+                if (s.sp[q].hi)
+                    for (int64_t e = e0 + 8 * t; e < e1; e += 8 * 256) {
+                        *reinterpret_cast<uint4*>(s.sp[q].hi + e) = make_uint4(0, 0, 0, 0);
+                        *reinterpret_cast<uint4*>(s.sp[q].lo + e) = make_uint4(0, 0, 0, 0);
+                    }
+            continue;
+        }
+    }
     unsigned mask = 0;
     int cnt = 0;
     if (row < a.n_out) {
-        #pragma unroll
-        for (int k = 0; k < KV; ++k) {
-            const int n = __ldg(a.nbr + (size_t)k * a.n_out + row);
-            if (n >= 0) { list[cnt * 256 + t] = n; mask |= 1u << k; ++cnt; }
+        if (UP) {
+            const int p = __ldg(s.up_parent + row);
+            if (p >= 0) { list[t] = p; mask = 1u << __ldg(s.up_koff + row); cnt = 1; }
+        } else {
+            #pragma unroll
+            for (int k = 0; k < KV; ++k) {
+                const int n = __ldg(a.nbr + (size_t)k * a.n_out + row);
+                if (n >= 0) { list[cnt * 256 + t] = n; mask |= 1u << k; ++cnt; }
+            }
         }
     }
-    __syncthreads();
+    // (the list column of thread t is written and read by thread t only: no barrier)
 
     float2 acc[CO / 2];
     #pragma unroll
     for (int c = 0; c < CO / 2; ++c) acc[c] = make_float2(0.0f, 0.0f);
-    float4 x[CI / 4], xn[CI / 4];
-    if (cnt > 0) {
-        const float4* p = reinterpret_cast<const float4*>(a.inA + (size_t)list[t] * CI);
+    auto src_ptr = [&](int n, int c0) -> const float4* {
+        if (CAT) return reinterpret_cast<const float4*>((c0 < CA ? a.inA + (size_t)n * CA + c0 : a.inB + (size_t)n * CA + (c0 - CA)));
+        return reinterpret_cast<const float4*>(a.inA + (size_t)n * CI + c0);
+    };
+    float4 xn[PREF ? CI / 4 : 1];
+    if (PREF && cnt > 0) {
+        const int n = list[t];
         #pragma unroll
-        for (int c = 0; c < CI / 4; ++c) xn[c] = __ldg(p + c);
+        for (int c = 0; c < CI / 4; ++c) xn[c] = __ldg(src_ptr(n, 4 * c));
     }
     for (int i = 0; i < cnt; ++i) {
-        #pragma unroll
-        for (int c = 0; c < CI / 4; ++c) x[c] = xn[c];
-        if (i + 1 < cnt) {                               // next neighbour's features in flight while this one is multiplied
-            const float4* p = reinterpret_cast<const float4*>(a.inA + (size_t)list[(i + 1) * 256 + t] * CI);
+        float4 x[PREF ? CI / 4 : 1];
+        int n_cur = 0;
+        if (PREF) {
             #pragma unroll
-            for (int c = 0; c < CI / 4; ++c) xn[c] = __ldg(p + c);
+            for (int c = 0; c < CI / 4; ++c) x[c] = xn[c];
+            if (i + 1 < cnt) {                           // next neighbour's features in flight while this one is multiplied
+                const int n = list[(i + 1) * 256 + t];
+                #pragma unroll
+                for (int c = 0; c < CI / 4; ++c) xn[c] = __ldg(src_ptr(n, 4 * c));
+            }
+        } else {
+            n_cur = list[i * 256 + t];
         }
         const int k = __ffs(mask) - 1;
         mask &= mask - 1;
         const float* wk = sw + k * WS;
         #pragma unroll
         for (int c0 = 0; c0 < CI; c0 += 4) {
-            float4 v = x[c0 / 4];
+            float4 v = PREF ? x[PREF ? c0 / 4 : 0] : __ldg(src_ptr(n_cur, c0));
             if (BN) {
                 v.x = fmaxf(fmaf(v.x, sbn[c0 + 0], sbn[CI + c0 + 0]), 0.0f);
                 v.y = fmaxf(fmaf(v.y, sbn[c0 + 1], sbn[CI + c0 + 1]), 0.0f);
@@ -342,44 +386,106 @@ __global__ void __launch_bounds__(256) k_conv_sp8(ConvArgs a) {
             }
             #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
-                const float s = comp4(v, cc);
-                const float2 ss = make_float2(s, s);
-                const float4 w0 = *reinterpret_cast<const float4*>(wk + (c0 + cc) * CO);
-                const float4 w1 = *reinterpret_cast<const float4*>(wk + (c0 + cc) * CO + 4);
-                acc[0] = __ffma2_rn(ss, make_float2(w0.x, w0.y), acc[0]);
-                acc[1] = __ffma2_rn(ss, make_float2(w0.z, w0.w), acc[1]);
-                acc[2] = __ffma2_rn(ss, make_float2(w1.x, w1.y), acc[2]);
-                acc[3] = __ffma2_rn(ss, make_float2(w1.z, w1.w), acc[3]);
+                const float sv = comp4(v, cc);
+                const float2 ss = make_float2(sv, sv);
+                const float* wrow = wk + (c0 + cc) * CO;
+                #pragma unroll
+                for (int q = 0; q < CO / 4; ++q) {
+                    const float4 wv = *reinterpret_cast<const float4*>(wrow + 4 * q);
+                    acc[2 * q + 0] = __ffma2_rn(ss, make_float2(wv.x, wv.y), acc[2 * q + 0]);
+                    acc[2 * q + 1] = __ffma2_rn(ss, make_float2(wv.z, wv.w), acc[2 * q + 1]);
+                }
             }
         }
     }
-    if (row >= a.n_out) return;
+    if (row >= a.n_out) continue;
     const size_t o = (size_t)row * CO;
     const bool take_src = a.sel_flag && a.sel_flag[row] == 0;
     #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        float4 r = make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
+    for (int q = 0; q < CO / 8; ++q) {
+        float r[8] = {acc[4 * q].x, acc[4 * q].y, acc[4 * q + 1].x, acc[4 * q + 1].y,
+                      acc[4 * q + 2].x, acc[4 * q + 2].y, acc[4 * q + 3].x, acc[4 * q + 3].y};
+        const int ch = 8 * q;
         if (a.res) {
-            const float4 e = *reinterpret_cast<const float4*>(a.res + o + 4 * q);
-            r.x += e.x; r.y += e.y; r.z += e.z; r.w += e.w;
+            const float4 e0 = *reinterpret_cast<const float4*>(a.res + o + ch), e1 = *reinterpret_cast<const float4*>(a.res + o + ch + 4);
+            r[0] += e0.x; r[1] += e0.y; r[2] += e0.z; r[3] += e0.w; r[4] += e1.x; r[5] += e1.y; r[6] += e1.z; r[7] += e1.w;
         }
-        if (take_src) r = *reinterpret_cast<const float4*>(a.sel_src + o + 4 * q);
-        *reinterpret_cast<float4*>(a.out + o + 4 * q) = r;
+        if (take_src) {
+            const float4 e0 = *reinterpret_cast<const float4*>(a.sel_src + o + ch), e1 = *reinterpret_cast<const float4*>(a.sel_src + o + ch + 4);
+            r[0] = e0.x; r[1] = e0.y; r[2] = e0.z; r[3] = e0.w; r[4] = e1.x; r[5] = e1.y; r[6] = e1.z; r[7] = e1.w;
+        }
+        if (a.out) {
+            *reinterpret_cast<float4*>(a.out + o + ch) = make_float4(r[0], r[1], r[2], r[3]);
+            *reinterpret_cast<float4*>(a.out + o + ch + 4) = make_float4(r[4], r[5], r[6], r[7]);
+        }
+        #pragma unroll
+        for (int u = 0; u < 2; ++u) {                    // the consumers' BN + ReLU + FP16 hi/lo split (conv_tc.cu epilogue)
+            if (!s.sp[u].hi) continue;
+            float x[8];
+            float mx = 0.f;
+            #pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                x[i] = s.sp[u].alpha ? fmaxf(fmaf(r[i], s.sp[u].alpha[ch + i], s.sp[u].beta[ch + i]), 0.f) : r[i];
+                mx = fmaxf(mx, fabsf(x[i]));
+            }
+            if (!(mx < 3.0e4f)) *s.range_flag = 1;
+            uint32_t hw[4], lw[4];
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+                const float2 f = __half22float2(h);
+                const __half2 l = __floats2half2_rn(x[2 * i] - f.x, x[2 * i + 1] - f.y);
+                hw[i] = *reinterpret_cast<const uint32_t*>(&h);
+                lw[i] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            *reinterpret_cast<uint4*>(s.sp[u].hi + o + ch) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(s.sp[u].lo + o + ch) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
     }
+  }
 }
 
-template <int CI, bool BN>
-static void launch_conv_sp8(Ctx& cx, const ConvArgs& a) {
-    if (a.n_out <= 0) return;
-    const size_t smem = (size_t)(16 + 27 * (CI * 8 + 4)) * 4 + (size_t)27 * 256 * 4;
-    auto kern = k_conv_sp8<CI, BN>;
-    static bool attr_set = false;
-    if (!attr_set) {
+template <int CI, int CO, int KV, bool BN, bool CAT, bool UP>
+static void launch_conv_sp(Ctx& cx, const SpArgs& s) {
+    if (s.c.n_out <= 0) return;
+    const size_t smem = (size_t)(128 + KV * (CI * CO + 4)) * 4 + (size_t)(UP ? 1 : KV) * 256 * 4;
+    auto kern = k_conv_sp<CI, CO, KV, BN, CAT, UP>;
+    static int per_sm = 0;
+    if (!per_sm) {
         SQSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        SQSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+        if (per_sm < 1) per_sm = 1;
     }
-    kern<<<div_up(a.n_out, 256), 256, smem, cx.st>>>(a);
+    const int grid = (int)std::min<int64_t>(div_up(s.c.n_out, 256), (int64_t)kNumSMs * per_sm);
+    kern<<<grid, 256, smem, cx.st>>>(s);
     cx.launches++;
+}
+
+// shapes served by the sparse-loop kernel
+static bool conv_sparse_supported(const ConvW& w, bool cat, bool up) {
+    const bool bn = w.bn != nullptr;
+    // inverse convolutions: measured per C3 step 7.2 vs 24.2 ms (16 -> 8) and 18.7 vs 26.2 ms (32 -> 16) against the tensor-core
+    // gather conv, but 36.0 vs 23.0 ms at 64 -> 32 (512 per-lane float4 weight reads per row): that one stays on the tensor cores
+    if (up) return bn && w.kv == 8 && ((w.ci == 16 && w.co == 8) || (w.ci == 32 && w.co == 16) ||
+                                       (w.ci == 64 && w.co == 32 && getenv("SQSM_UP_SPARSE_ALL") != nullptr));
+    if (w.kv == 27 && w.co == 8) return (w.ci == 4 && !bn && !cat) || (w.ci == 8 && bn && !cat) || (w.ci == 16 && bn && cat);
+    return w.kv == 8 && w.ci == 8 && w.co == 16 && bn && !cat;
+}
+
+static bool conv_sparse(Ctx& cx, const ConvW& w, bool cat, bool up, const SpArgs& s) {
+    if (!conv_sparse_supported(w, cat, up)) return false;
+    if (up) {
+        if (w.ci == 16) launch_conv_sp<16, 8, 8, true, false, true>(cx, s);
+        else if (w.ci == 32) launch_conv_sp<32, 16, 8, true, false, true>(cx, s);
+        else launch_conv_sp<64, 32, 8, true, false, true>(cx, s);
+    } else if (w.kv == 27) {
+        if (w.ci == 4) launch_conv_sp<4, 8, 27, false, false, false>(cx, s);
+        else if (w.ci == 8) launch_conv_sp<8, 8, 27, true, false, false>(cx, s);
+        else launch_conv_sp<16, 8, 27, true, true, false>(cx, s);
+    } else {
+        launch_conv_sp<8, 16, 8, true, false, false>(cx, s);
+    }
+    return true;
 }
 
 // ---------------------------------------------------------------------------------- heads + contraction
@@ -602,12 +708,6 @@ std::vector<float> make_tc_weight_image_f16(const float* w_kcico, int kv, int ci
 
 static bool conv_ffma(Ctx& cx, const ConvW& w, bool cat, const ConvArgs& a) {
     const bool bn = w.bn != nullptr;
-    // level-0 SubM layers: per-row loop over the present offsets (SQSM_L0_DENSE=1 restores the dense 27-offset kernel)
-    const bool sparse_l0 = getenv("SQSM_L0_DENSE") == nullptr;
-    if (sparse_l0 && w.kv == 27 && w.co == 8 && !cat && a.nbr) {
-        if (w.ci == 8 && bn) { launch_conv_sp8<8, true>(cx, a); return true; }
-        if (w.ci == 4 && !bn) { launch_conv_sp8<4, false>(cx, a); return true; }
-    }
 #define SQSM_FF_CASE(CI_, CO_, KV_, BN_, CAT_)                                                    \
     if (w.ci == CI_ && w.co == CO_ && w.kv == KV_ && bn == BN_ && cat == CAT_) {                  \
         conv_dispatch<CI_, CO_, KV_, BN_, CAT_>(cx, a);                                           \
@@ -637,8 +737,17 @@ static bool tc_f16_layer(const NetWeights& nw, const ConvW& w) { return nw.mode 
 
 // tensor cores from tc_min_co output channels up, plus the level-0 decoder conv on the concatenated 16 channels
 // (16 -> 8, 27 offsets: 51 vs 66 ms per C3 step on FFMA; the other 8-channel layers are faster on FFMA)
+// SQSM_SPARSE_LOOP=0 turns the sparse-loop FFMA kernel (k_conv_sp) off: level 0 and the inverse convolutions then run as in
+// round 1 / early round 2 (dense 27-offset FFMA kernel, tensor-core 16 -> 8 concat conv and inverse convolutions)
+static bool sparse_loop_on() {
+    const char* e = getenv("SQSM_SPARSE_LOOP");
+    return !(e && e[0] == '0');
+}
+
 static bool layer_uses_tc(const NetWeights& nw, const ConvW& w, bool cat) {
-    return nw.mode != 0 && w.wimg && (w.co >= nw.tc_min_co || (nw.mode >= 3 && cat && w.ci == 16 && w.co == 8 && w.kv == 27));
+    if (nw.mode == 0 || !w.wimg) return false;
+    if (sparse_loop_on() && conv_sparse_supported(w, cat, false)) return false;     // level 0 and its down convolution
+    return w.co >= nw.tc_min_co || (nw.mode >= 3 && cat && w.ci == 16 && w.co == 8 && w.kv == 27);
 }
 
 struct ConvOpts {
@@ -654,6 +763,7 @@ struct ConvOpts {
     const int32_t* up_parent = nullptr;  // inverse convolution (kv = 8): rulebook from the down-sample tables
     const int32_t* up_koff = nullptr;
     const struct TileNeed* need = nullptr;   // decoder layers: only these tiles of 128 output rows are computed
+    bool up_on_tc = false;               // inverse convolution on the tensor-core kernel (SQSM_UPCONV_TC=1) instead of k_conv_sp
 };
 
 // Which 128-row tiles of a level can influence an interior output (see need_tiles() below).
@@ -687,7 +797,8 @@ static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, boo
     for (int q = 0; q < 2; ++q) if (op.produce[q]) op.produce[q]->ready = false;
     if (n_out <= 0) return;
     const bool up = op.up_parent != nullptr;
-    const bool use_tc = up ? (nw.mode == 3 && w.wimg16) : layer_uses_tc(nw, w, cat);
+    const bool sparse = sparse_loop_on() && conv_sparse_supported(w, cat, up) && !(up && op.up_on_tc);
+    const bool use_tc = !sparse && (up ? (nw.mode == 3 && w.wimg16) : layer_uses_tc(nw, w, cat));
     // per-kernel scope: algorithmic bytes of SURVEY 8(d): features in + out, rulebook entries, residual re-read
     char fam[64];
     snprintf(fam, sizeof(fam), "conv_%s%s_ci%d_co%d_k%d", use_tc ? "tc" : "ffma", up ? "_up" : "", w.ci, w.co, w.kv);
@@ -775,11 +886,36 @@ static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, boo
         for (int q = 0; q < 2; ++q) if (op.produce[q]) op.produce[q]->ready = false;
         if (up) throw CudaError("no tensor-core kernel for inverse convolution " + name);
     }
-    ProfScope ps(cx, fam, alg_bytes, 0.0);
     ConvArgs ar;
     ar.inA = inA; ar.inB = inB; ar.nbr = nbr; ar.w = w.w; ar.bn = w.bn; ar.res = op.res; ar.sel_src = op.sel_src;
     ar.sel_flag = op.sel_flag; ar.out = out; ar.n_out = (int)n_out; ar.kc = 0;
     ar.tile_need = (op.need && op.need->valid) ? op.need->flag.p : nullptr;
+    if (sparse) {
+        SpArgs sa;
+        std::memset(&sa, 0, sizeof(sa));
+        sa.up_parent = op.up_parent; sa.up_koff = op.up_koff; sa.range_flag = nw.range_flag;
+        bool any_fused = false;
+        if (nw.mode == 3) {
+            for (int q = 0; q < 2; ++q) {
+                if (!op.produce[q]) continue;
+                const int64_t oe = (n_out * w.co + 1) / 2;
+                op.produce[q]->hi.alloc(oe, cx.st);
+                op.produce[q]->lo.alloc(oe, cx.st);
+                op.produce[q]->ready = true;
+                sa.sp[q].hi = reinterpret_cast<__half*>(op.produce[q]->hi.p);
+                sa.sp[q].lo = reinterpret_cast<__half*>(op.produce[q]->lo.p);
+                sa.sp[q].alpha = op.p_alpha[q]; sa.sp[q].beta = op.p_beta[q];
+                any_fused = true;
+            }
+        }
+        if (any_fused && !op.need_fp32) ar.out = nullptr;
+        sa.c = ar;
+        ProfScope ps(cx, fam, alg_bytes, 0.0);
+        if (conv_sparse(cx, w, cat, up, sa)) return;
+        throw CudaError("no sparse-loop kernel for layer " + name);
+    }
+    if (up) throw CudaError("inverse convolution " + name + ": neither the sparse-loop nor the tensor-core kernel applies");
+    ProfScope ps(cx, fam, alg_bytes, 0.0);
     if (!conv_ffma(cx, w, cat, ar)) throw CudaError("no convolution kernel for layer " + name);
 }
 
@@ -892,7 +1028,16 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
     DBuf<float> enc[kLevels], tmp[kLevels];
     // FP16 split mode: producers write their consumers' operands (FusedSplit); inverse convolutions on the tensor cores
     const bool fuse = nw.mode == 3 && getenv("SQSM_NO_FUSED_SPLIT") == nullptr;
-    const bool up_on_tc = nw.mode == 3 && getenv("SQSM_UPCONV_FFMA") == nullptr;
+    // inverse convolutions: sparse-loop FFMA kernel (default), tensor-core gather conv (SQSM_UPCONV_TC=1, or when the sparse
+    // loop is off) or the offset-bucketed FFMA kernel of round 1 (SQSM_UPCONV_FFMA=1)
+    const bool up_bucketed = getenv("SQSM_UPCONV_FFMA") != nullptr;
+    const bool up_all_tc = nw.mode == 3 && !up_bucketed && (getenv("SQSM_UPCONV_TC") != nullptr || !sparse_loop_on());
+    auto up_sparse_at = [&](int lvl) {
+        return !up_bucketed && !up_all_tc && sparse_loop_on() && conv_sparse_supported(nw.conv.at("L" + std::to_string(lvl) + ".up"), false, true);
+    };
+    auto up_tc_at = [&](int lvl) {
+        return nw.mode == 3 && !up_bucketed && nw.conv.at("L" + std::to_string(lvl) + ".up").wimg16 && !up_sparse_at(lvl);
+    };
     FusedSplit sp_in;                        // operands of the level's first convolution, written by the down convolution
     FusedSplit sp_down[kLevels];             // enc[l] as operands of the down convolution of level l
     FusedSplit sp_skip[kLevels];             // enc[l] as operands (first half of the concat) of tail.a of level l
@@ -941,7 +1086,7 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
             ConvOpts ob;
             ob.res = cur_in.p;
             ob.consume = &sp_mid;
-            if (fuse && deepest && l > 0 && up_on_tc) {
+            if (fuse && deepest && l > 0 && up_tc_at(l - 1)) {
                 // the deepest level feeds the inverse convolution only: its epilogue writes that layer's operands
                 const ConvW& wu = nw.conv.at("L" + std::to_string(l - 1) + ".up");
                 ob.produce[0] = &sp_cur; ob.p_alpha[0] = bn_a(wu, 0); ob.p_beta[0] = bn_b(wu, 0);
@@ -967,7 +1112,9 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
             // (k = 8 convolutions are bound by their epilogue: writing the next layer's operands there costs more than the
             // separate split pass saves - measured 23.6 -> 37.1 ms per C3 step against 7.5 ms of act_split)
             static const bool fuse_down = getenv("SQSM_FUSE_DOWN") != nullptr;
-            if (fuse && fuse_down && tc_f16_layer(nw, wn)) { od.produce[0] = &sp_in; od.p_alpha[0] = bn_a(wn, 0); od.p_beta[0] = bn_b(wn, 0); }
+            // the sparse-loop kernel (level 0 -> 1) holds a whole output row per thread: there the operand stores are cheap
+            const bool down_sparse = sparse_loop_on() && conv_sparse_supported(nw.conv.at(L + ".down"), false, false);
+            if (fuse && (fuse_down || down_sparse) && tc_f16_layer(nw, wn)) { od.produce[0] = &sp_in; od.p_alpha[0] = bn_a(wn, 0); od.p_beta[0] = bn_b(wn, 0); }
             conv_any(cx, nw, L + ".down", false, enc[l].p, nullptr, lv[l].child.p, nxt.p, nn, n, od);
             sp_down[l] = FusedSplit();
             cur_in = std::move(nxt);
@@ -987,7 +1134,7 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
         FusedSplit up_raw, up_act;           // the decoder half of the concat as operands of tail.i (raw) and tail.a (BN + ReLU)
         {
             ProfScope pt(cx, "down_up", 4.0 * (nc * cn + n * c) + 4.0 * n, 2.0 * (double)n * c * cn);
-            if (up_on_tc && wu.wimg16) {
+            if (up_tc_at(l) || up_sparse_at(l)) {
                 // SparseInverseConv3d as a gather convolution with 8 offsets: the rulebook entry (k, fine row) exists for
                 // k == koff[row] only (App. A); rows without a parent gather nothing and come out as 0 / relu(beta)
                 const bool i_tc = layer_uses_tc(nw, wi, true), a_tc = layer_uses_tc(nw, wa, true);
@@ -999,6 +1146,7 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
                 if (fuse && a_tc) { ou.produce[1] = &up_act; ou.p_alpha[1] = bn_a(wa, c); ou.p_beta[1] = bn_b(wa, c); }
                 ou.need_fp32 = !(fuse && i_tc && a_tc);
                 ou.need = &need[l];
+                ou.up_on_tc = up_tc_at(l);
                 if (ou.need_fp32) up.alloc(n * c, st);
                 conv_any(cx, nw, L + ".up", false, cur.p, nullptr, nullptr, up.p, n, nc, ou);
             } else {
@@ -1031,7 +1179,7 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
             ob.res = res.p; ob.sel_src = enc[l].p; ob.sel_flag = lv[l].row_desc.p;
             ob.consume = &sp_mid;
             ob.need = &need[l];
-            if (fuse && l > 0 && up_on_tc) {
+            if (fuse && l > 0 && up_tc_at(l - 1)) {
                 const ConvW& wn = nw.conv.at("L" + std::to_string(l - 1) + ".up");
                 ob.produce[0] = &sp_cur; ob.p_alpha[0] = bn_a(wn, 0); ob.p_beta[0] = bn_b(wn, 0);
                 ob.need_fp32 = keep;

@@ -568,10 +568,13 @@ def test_radius_graph_in_chunks(monkeypatch):
 
 
 def test_inverse_conv_paths_agree(leafoff_state, small_tree, monkeypatch):
-    """The tensor-core inverse convolution (dense GEMM + scatter, upconv_tc.cu) and the FFMA kernel give the same state
-    within the split-mode tolerance; both are checked against the oracle by check_iteration."""
+    """The three inverse-convolution kernels - sparse-loop FFMA (default), offset-bucketed FFMA and the tensor-core gather
+    conv - are each checked against the oracle by check_iteration."""
     check_iteration(leafoff_state, small_tree)
     monkeypatch.setenv("SQSM_UPCONV_FFMA", "1")
+    check_iteration(leafoff_state, small_tree)
+    monkeypatch.delenv("SQSM_UPCONV_FFMA")
+    monkeypatch.setenv("SQSM_UPCONV_TC", "1")
     check_iteration(leafoff_state, small_tree)
 
 
@@ -597,25 +600,28 @@ def test_decoder_tile_skipping_is_bit_identical(leafoff_state, monkeypatch, mode
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
 
 
-def test_level0_sparse_loop_equals_dense_kernel(leafoff_state, small_tree, monkeypatch):
-    """Level-0 SubM layers: the kernel that walks only a row's present offsets (k_conv_sp8) accumulates in the same order
-    as the dense 27-offset kernel (absent neighbours add exact zeros there), so the states must be bit-identical; both
-    are within tolerance of the oracle (check_iteration)."""
+def test_sparse_loop_kernel_against_dense_paths(leafoff_state, small_tree, monkeypatch):
+    """Level 0, its down convolution and the inverse convolutions run on the kernel that walks only a row's present offsets
+    (k_conv_sp).  With SQSM_SPARSE_LOOP=0 the same layers take the dense 27-offset FFMA kernel / the tensor-core kernels:
+    both settings must agree with the oracle (check_iteration) and with each other within the split-mode tolerance, and
+    take the same accept / reject decisions."""
     from smartqsm_b200.synthetic import make_tree
-    check_iteration(leafoff_state, small_tree)
     pts = make_tree(200000, 12, True)
     outs = []
-    for dense in (False, True):
-        if dense:
-            monkeypatch.setenv("SQSM_L0_DENSE", "1")
+    for sparse in (True, False):
+        if sparse:
+            monkeypatch.delenv("SQSM_SPARSE_LOOP", raising=False)
         else:
-            monkeypatch.delenv("SQSM_L0_DENSE", raising=False)
+            monkeypatch.setenv("SQSM_SPARSE_LOOP", "0")
+        check_iteration(leafoff_state, small_tree)
         eng = make_engine(leafoff_state, monitored_by_chamfer_distance=True)
         eng.set_points(pts)
-        stats = [eng.contract_step() for _ in range(3)]
-        P, D = eng.result()
-        outs.append((P, D, [(s["n_out"], s["accepted"], s["chamfer"]) for s in stats]))
-    check_iteration(leafoff_state, small_tree)           # dense kernel against the oracle as well
-    monkeypatch.delenv("SQSM_L0_DENSE", raising=False)
+        stats = [eng.contract_step()]
+        P, D = eng.result()                              # after ONE thunk the row set is fixed by the input voxelisation
+        stats += [eng.contract_step() for _ in range(2)]
+        outs.append((P, D, [s["accepted"] for s in stats], [s["n_out"] for s in stats], [s["chamfer"] for s in stats]))
+    monkeypatch.delenv("SQSM_SPARSE_LOOP", raising=False)
     assert outs[0][2] == outs[1][2]
-    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert outs[0][3][0] == outs[1][3][0] and np.allclose(outs[0][3], outs[1][3], rtol=1e-3)
+    assert np.allclose(outs[0][4], outs[1][4], rtol=1e-3)
+    assert np.abs(outs[0][0] - outs[1][0]).max() < 1e-4 and np.abs(outs[0][1] - outs[1][1]).max() < 1e-4
