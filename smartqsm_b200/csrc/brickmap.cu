@@ -179,20 +179,23 @@ static uint32_t next_pow2(uint64_t v) {
 }
 
 void brickmap_build(Ctx& cx, BrickMap& m, const uint64_t* d_ent_key, const uint16_t* d_ent_pos, int64_t n_ent,
-                    int32_t* d_ent_brick) {
+                    int32_t* d_ent_brick, int64_t expected_bricks) {
     cudaStream_t st = cx.st;
     Trace tr(cx, "  brickmap_build");
     SQSM_CHECK(n_ent < (1ll << 31), "too many entries for one BrickMap build");
     m.n_bricks = 0;
     m.n_rows = 0;
     if (n_ent == 0) return;
-    // Expect far fewer bricks than entries (a brick holds up to 512 voxels): start with a table of about
-    // n_ent/2 slots (L2 resident for the sizes of this path) and retry with 4x if it exceeds 50 % load.
+    // Expect far fewer bricks than entries (a brick holds up to 512 voxels): start with a table of four slots per expected
+    // brick (callers pass what they know: about n_ent / 10 bricks for a 1 cm grid over a surface scan, a quarter of the finer
+    // level's bricks for a down-sampled level; default n_ent / 8) so that keys + values stay L2 resident, and retry with 4x
+    // if the table exceeds 50 % load.
     DBuf<uint64_t> list;
     DBuf<int32_t> counter(2, st);
     int grid = div_up(n_ent, 256);
     int32_t nb = 0;
-    uint64_t want = std::max<uint64_t>((uint64_t)n_ent / 2, 4096);
+    if (expected_bricks <= 0) expected_bricks = n_ent / 8;
+    uint64_t want = std::max<uint64_t>(4 * (uint64_t)std::min<int64_t>(expected_bricks, n_ent), 4096);
     for (int attempt = 0;; ++attempt) {
         m.cap = next_pow2(want);
         const int list_cap = (int)std::min<uint64_t>((uint64_t)m.cap / 2, (uint64_t)n_ent);

@@ -81,7 +81,7 @@ struct BrickMap {
 // kEmptyKey are ignored.  On return ent_brick[e] holds the brick id of every valid entry.
 // Synchronises the stream twice (brick count, row count).
 void brickmap_build(Ctx& cx, BrickMap& m, const uint64_t* d_ent_key, const uint16_t* d_ent_pos,
-                    int64_t n_ent, int32_t* d_ent_brick);
+                    int64_t n_ent, int32_t* d_ent_brick, int64_t expected_bricks = 0);
 
 // bnbr table (27 neighbour brick ids per brick); needed by the rulebook / NN / graph kernels.
 void brickmap_build_neighbours(Ctx& cx, BrickMap& m);

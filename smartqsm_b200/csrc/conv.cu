@@ -288,9 +288,12 @@ struct SpArgs {
     const int32_t* up_koff;
     SpOut sp[2];
     int* range_flag;
+    const uint32_t* csr_mask;    // CSR: compact rulebook (LevelTables::nbr_mask / nbr_off / nbr_list) instead of c.nbr
+    const uint32_t* csr_off;
+    const int32_t* csr_list;
 };
 
-template <int CI, int CO, int KV, bool BN, bool CAT, bool UP>
+template <int CI, int CO, int KV, bool BN, bool CAT, bool UP, bool CSR>
 __global__ void __launch_bounds__(256) k_conv_sp(SpArgs s) {
     const ConvArgs& a = s.c;
     constexpr int WS = CI * CO + 4;                      // padded floats per offset
@@ -299,7 +302,7 @@ __global__ void __launch_bounds__(256) k_conv_sp(SpArgs s) {
     extern __shared__ __align__(16) float smem[];
     float* sbn = smem;                                   // [2][CI]
     float* sw = smem + 2 * 64;                           // [KV][WS]
-    int32_t* list = reinterpret_cast<int32_t*>(sw + KV * WS);   // [LK][256] present neighbours of thread t, column t
+    int32_t* list = reinterpret_cast<int32_t*>(sw + KV * WS);   // [LK][256] present neighbours of thread t, column t (!CSR)
 
     const int t = threadIdx.x;
     // persistent blocks: the weight image is staged once per block, then the block walks 256-row groups
@@ -331,8 +334,13 @@ __global__ void __launch_bounds__(256) k_conv_sp(SpArgs s) {
     }
     unsigned mask = 0;
     int cnt = 0;
+    const int32_t* clist = nullptr;                      // CSR: the row's present neighbours, read straight from global memory
     if (row < a.n_out) {
-        if (UP) {
+        if (CSR) {
+            mask = __ldg(s.csr_mask + row);
+            cnt = __popc(mask);
+            clist = s.csr_list + __ldg(s.csr_off + row);
+        } else if (UP) {
             const int p = __ldg(s.up_parent + row);
             if (p >= 0) { list[t] = p; mask = 1u << __ldg(s.up_koff + row); cnt = 1; }
         } else {
@@ -352,11 +360,14 @@ __global__ void __launch_bounds__(256) k_conv_sp(SpArgs s) {
         if (CAT) return reinterpret_cast<const float4*>((c0 < CA ? a.inA + (size_t)n * CA + c0 : a.inB + (size_t)n * CA + (c0 - CA)));
         return reinterpret_cast<const float4*>(a.inA + (size_t)n * CI + c0);
     };
+    auto nb_at = [&](int i) -> int { return CSR ? __ldg(clist + i) : list[i * 256 + t]; };
     float4 xn[PREF ? CI / 4 : 1];
+    int n_ahead = 0;                                     // CSR: index of neighbour i + 2, in flight behind the features of i + 1
     if (PREF && cnt > 0) {
-        const int n = list[t];
+        const int n = nb_at(0);
         #pragma unroll
         for (int c = 0; c < CI / 4; ++c) xn[c] = __ldg(src_ptr(n, 4 * c));
+        if (CSR && cnt > 1) n_ahead = nb_at(1);
     }
     for (int i = 0; i < cnt; ++i) {
         float4 x[PREF ? CI / 4 : 1];
@@ -365,12 +376,13 @@ __global__ void __launch_bounds__(256) k_conv_sp(SpArgs s) {
             #pragma unroll
             for (int c = 0; c < CI / 4; ++c) x[c] = xn[c];
             if (i + 1 < cnt) {                           // next neighbour's features in flight while this one is multiplied
-                const int n = list[(i + 1) * 256 + t];
+                const int n = CSR ? n_ahead : nb_at(i + 1);
                 #pragma unroll
                 for (int c = 0; c < CI / 4; ++c) xn[c] = __ldg(src_ptr(n, 4 * c));
+                if (CSR && i + 2 < cnt) n_ahead = nb_at(i + 2);
             }
         } else {
-            n_cur = list[i * 256 + t];
+            n_cur = nb_at(i);
         }
         const int k = __ffs(mask) - 1;
         mask &= mask - 1;
@@ -445,11 +457,11 @@ __global__ void __launch_bounds__(256) k_conv_sp(SpArgs s) {
   }
 }
 
-template <int CI, int CO, int KV, bool BN, bool CAT, bool UP>
+template <int CI, int CO, int KV, bool BN, bool CAT, bool UP, bool CSR = false>
 static void launch_conv_sp(Ctx& cx, const SpArgs& s) {
     if (s.c.n_out <= 0) return;
-    const size_t smem = (size_t)(128 + KV * (CI * CO + 4)) * 4 + (size_t)(UP ? 1 : KV) * 256 * 4;
-    auto kern = k_conv_sp<CI, CO, KV, BN, CAT, UP>;
+    const size_t smem = (size_t)(128 + KV * (CI * CO + 4)) * 4 + (size_t)(CSR ? 0 : (UP ? 1 : KV)) * 256 * 4;
+    auto kern = k_conv_sp<CI, CO, KV, BN, CAT, UP, CSR>;
     static int per_sm = 0;
     if (!per_sm) {
         SQSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -472,12 +484,28 @@ static bool conv_sparse_supported(const ConvW& w, bool cat, bool up) {
     return w.kv == 8 && w.ci == 8 && w.co == 16 && bn && !cat;
 }
 
+static bool sparse_loop_on();
+bool net_level0_uses_csr(const NetWeights& nw) {
+    if (!sparse_loop_on() || getenv("SQSM_NO_CSR") != nullptr) return false;
+    static const char* names[5] = {"input", "L0.blk.a", "L0.blk.b", "L0.tail.a", "L0.tail.b"};
+    for (int i = 0; i < 5; ++i) {
+        auto it = nw.conv.find(names[i]);
+        if (it == nw.conv.end()) continue;
+        if (it->second.kv != 27 || !conv_sparse_supported(it->second, i == 3, false)) return false;
+    }
+    return true;
+}
+
 static bool conv_sparse(Ctx& cx, const ConvW& w, bool cat, bool up, const SpArgs& s) {
     if (!conv_sparse_supported(w, cat, up)) return false;
     if (up) {
         if (w.ci == 16) launch_conv_sp<16, 8, 8, true, false, true>(cx, s);
         else if (w.ci == 32) launch_conv_sp<32, 16, 8, true, false, true>(cx, s);
         else launch_conv_sp<64, 32, 8, true, false, true>(cx, s);
+    } else if (w.kv == 27 && s.csr_mask) {
+        if (w.ci == 4) launch_conv_sp<4, 8, 27, false, false, false, true>(cx, s);
+        else if (w.ci == 8) launch_conv_sp<8, 8, 27, true, false, false, true>(cx, s);
+        else launch_conv_sp<16, 8, 27, true, true, false, true>(cx, s);
     } else if (w.kv == 27) {
         if (w.ci == 4) launch_conv_sp<4, 8, 27, false, false, false>(cx, s);
         else if (w.ci == 8) launch_conv_sp<8, 8, 27, true, false, false>(cx, s);
@@ -764,6 +792,7 @@ struct ConvOpts {
     const int32_t* up_koff = nullptr;
     const struct TileNeed* need = nullptr;   // decoder layers: only these tiles of 128 output rows are computed
     bool up_on_tc = false;               // inverse convolution on the tensor-core kernel (SQSM_UPCONV_TC=1) instead of k_conv_sp
+    const LevelTables* csr = nullptr;    // level whose compact rulebook (nbr_mask / nbr_off / nbr_list) replaces `nbr`
 };
 
 // Which 128-row tiles of a level can influence an interior output (see need_tiles() below).
@@ -803,7 +832,7 @@ static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, boo
     char fam[64];
     snprintf(fam, sizeof(fam), "conv_%s%s_ci%d_co%d_k%d", use_tc ? "tc" : "ffma", up ? "_up" : "", w.ci, w.co, w.kv);
     const double alg_bytes = 4.0 * ((double)n_in * w.ci + (double)n_out * w.co) +
-                             4.0 * (up ? 2.0 * n_out : (nbr ? (double)w.kv * n_out : 0.0)) + (op.res ? 4.0 * (double)n_out * w.co : 0.0);
+                             4.0 * (up ? 2.0 * n_out : ((nbr || op.csr) ? (double)w.kv * n_out : 0.0)) + (op.res ? 4.0 * (double)n_out * w.co : 0.0);
     static const char* tma_only = getenv("SQSM_TMA_ONLY");        // debug: restrict the TMA kernel to layers whose name contains this
     if (use_tc && !up && nw.mode == 4 && w.wimg_tma && conv_tma_supported(w.ci, w.co, w.kv, cat) &&
         (!tma_only || name.find(tma_only) != std::string::npos)) {
@@ -894,6 +923,10 @@ static void conv_any(Ctx& cx, const NetWeights& nw, const std::string& name, boo
         SpArgs sa;
         std::memset(&sa, 0, sizeof(sa));
         sa.up_parent = op.up_parent; sa.up_koff = op.up_koff; sa.range_flag = nw.range_flag;
+        if (op.csr && op.csr->nbr_mask.p && w.kv == 27) {
+            sa.csr_mask = op.csr->nbr_mask.p; sa.csr_off = op.csr->nbr_off.p; sa.csr_list = op.csr->nbr_list.p;
+        }
+        if (w.kv == 27 && !sa.csr_mask && !nbr) throw CudaError("layer " + name + ": no rulebook (neither dense nor compact)");
         bool any_fused = false;
         if (nw.mode == 3) {
             for (int q = 0; q < 2; ++q) {
@@ -1064,7 +1097,9 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
     DBuf<float> cur_in(n0 * 8, st);
     {
         ProfScope pt(cx, "subm_l0", 4.0 * n0 * (3 + 8) + 4.0 * 27 * n0, 2.0 * (double)lv[0].pairs * 3 * 8);
-        conv_any(cx, nw, "input", false, (const float*)rows.xyz.p, nullptr, lv[0].nbr.p, cur_in.p, n0, n0);
+        ConvOpts oi;
+        oi.csr = &lv[0];
+        conv_any(cx, nw, "input", false, (const float*)rows.xyz.p, nullptr, lv[0].nbr.p, cur_in.p, n0, n0, oi);
     }
     if (keep) keep_copy(cx, fb, "input_conv", cur_in.p, n0, 8, 0);
     for (int l = 0; l < n_levels; ++l) {
@@ -1082,6 +1117,7 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
             ConvOpts oa;
             oa.consume = &sp_in;
             if (fuse && tc_f16_layer(nw, wb)) { oa.produce[0] = &sp_mid; oa.p_alpha[0] = bn_a(wb, 0); oa.p_beta[0] = bn_b(wb, 0); oa.need_fp32 = false; }
+            oa.csr = &lv[l];
             conv_any(cx, nw, L + ".blk.a", false, cur_in.p, nullptr, lv[l].nbr.p, tmp[l].p, n, n, oa);
             ConvOpts ob;
             ob.res = cur_in.p;
@@ -1098,6 +1134,7 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
                 if (layer_uses_tc(nw, wd, false)) { ob.produce[0] = &sp_down[l]; ob.p_alpha[0] = bn_a(wd, 0); ob.p_beta[0] = bn_b(wd, 0); }
                 if (layer_uses_tc(nw, wa, true)) { ob.produce[1] = &sp_skip[l]; ob.p_alpha[1] = bn_a(wa, 0); ob.p_beta[1] = bn_b(wa, 0); }
             }
+            ob.csr = &lv[l];
             conv_any(cx, nw, L + ".blk.b", false, tmp[l].p, nullptr, lv[l].nbr.p, enc[l].p, n, n, ob);
         }
         sp_in = FusedSplit();
@@ -1171,6 +1208,7 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
             oa.consumeB = &up_act;
             oa.need = &need[l];
             if (fuse && tc_f16_layer(nw, wb)) { oa.produce[0] = &sp_mid; oa.p_alpha[0] = bn_a(wb, 0); oa.p_beta[0] = bn_b(wb, 0); oa.need_fp32 = false; }
+            oa.csr = &lv[l];
             conv_any(cx, nw, L + ".tail.a", true, enc[l].p, up.p, lv[l].nbr.p, tmp[l].p, n, n, oa);
             sp_skip[l] = FusedSplit();
             up_act = FusedSplit();
@@ -1184,6 +1222,7 @@ void net_forward(Ctx& cx, const NetWeights& nw, LevelTables* lv, const Level0Row
                 ob.produce[0] = &sp_cur; ob.p_alpha[0] = bn_a(wn, 0); ob.p_beta[0] = bn_b(wn, 0);
                 ob.need_fp32 = keep;
             }
+            ob.csr = &lv[l];
             conv_any(cx, nw, L + ".tail.b", false, tmp[l].p, nullptr, lv[l].nbr.p, out.p, n, n, ob);
         }
         if (keep) keep_copy(cx, fb, "dec" + std::to_string(l), out.p, n, c, l);

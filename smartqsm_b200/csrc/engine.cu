@@ -412,7 +412,13 @@ static void step_begin(sqsm_engine* h, int shard, int n_shards, SqsmIterStats& s
         ProfScope* rs = new ProfScope(cx, "rulebook", 0.0, 0.0);
         T.mark();
         int64_t far = 0;
-        { Trace tr(cx, "build_subm L0"); build_subm(cx, lv[0], batch0, nb, cfg.batch_size, &far); }
+        {
+            // level 0: the compact rulebook when every 27-offset layer of the level runs on the sparse-loop kernel; the dense
+            // table in addition only for the debug capture (the parity tests compare it with the oracle's)
+            Trace tr(cx, "build_subm L0");
+            const bool csr = net_level0_uses_csr(h->nw);
+            build_subm(cx, lv[0], batch0, nb, cfg.batch_size, &far, !csr || h->capture, csr);
+        }
         s.far_face_rows += far;
         int n_levels = 1;
         for (int l = 0; l + 1 < kLevels; ++l) {

@@ -29,7 +29,12 @@ struct LevelTables {
     int64_t n = 0;                      // rows
     DBuf<int32_t>  row_brick;           // [n]
     DBuf<uint16_t> row_pos;             // [n]
-    DBuf<int32_t>  nbr;                 // [27][n]  SubM rulebook, output-stationary: input row or -1
+    DBuf<int32_t>  nbr;                 // [27][n]  SubM rulebook, output-stationary: input row or -1 (absent when only
+                                        //          the compact form below is wanted)
+    // compact (CSR) form of the same rulebook for the sparse-loop kernel (level 0: 5 of 27 neighbours exist):
+    DBuf<uint32_t> nbr_mask;            // [n] bit k = kernel offset k present
+    DBuf<uint32_t> nbr_off;             // [n] first entry of the row in nbr_list
+    DBuf<int32_t>  nbr_list;            // present input rows, ascending kernel offset inside a row
     DBuf<int32_t>  parent;              // [n]      coarse row or -1              (levels 0..2)
     DBuf<int32_t>  koff;                // [n]      kz*4+ky*2+kx                  (levels 0..2)
     DBuf<int32_t>  child;               // [8][n_next] fine row or -1 (down conv, output-stationary)
@@ -120,7 +125,9 @@ struct VoxelStats { int64_t far_face = 0; };
 void build_level0(Ctx& cx, const float* d_P, const float* d_D, const TilingResult& tl, int s0, int s1,
                   int batch_size, float voxel_size, LevelTables& L0, Level0Rows& rows, int64_t out_base,
                   int64_t* n_out, DBuf<int32_t>& ent_row_out);
-void build_subm(Ctx& cx, LevelTables& L, int batch0, int n_batches, int batch_size, int64_t* far_face);
+void build_subm(Ctx& cx, LevelTables& L, int batch0, int n_batches, int batch_size, int64_t* far_face,
+                bool want_dense = true, bool want_csr = false);
+bool net_level0_uses_csr(const struct NetWeights& nw);     // conv.cu: the level-0 layers run on the sparse-loop kernel
 bool build_down(Ctx& cx, LevelTables& L, LevelTables& Lnext, int batch0, int n_batches, int batch_size);
 
 // spatial.cu

@@ -121,7 +121,7 @@ static void grid_build(Ctx& cx, const float* d_P, int64_t n, const double mn[3],
     err.zero();
     k_grid_entries<<<div_up(n, 256), 256, 0, st>>>(d_P, n, gm.g, ent_key.p, gm.ent_pos.p, err.p);
     cx.launches++;
-    brickmap_build(cx, gm.map, ent_key.p, gm.ent_pos.p, n, gm.ent_brick.p);
+    brickmap_build(cx, gm.map, ent_key.p, gm.ent_pos.p, n, gm.ent_brick.p, n / 16);
     int32_t herr = 0;
     SQSM_CUDA(cudaMemcpyAsync(&herr, err.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     gm.pt_row.alloc(n, st);
@@ -306,6 +306,12 @@ __device__ __forceinline__ float nn_gap2(int nb, const float* gm2, const float* 
     return ((dx == 0 ? 0.f : (dx < 0 ? gm2[0] : gp2[0])) + (dy == 0 ? 0.f : (dy < 0 ? gm2[1] : gp2[1])) +
             (dz == 0 ? 0.f : (dz < 0 ? gm2[2] : gp2[2]))) * 0.999999f;
 }
+// exact squared distance in float64, one fixed operation order for every kernel of the search (bit-identical results)
+__device__ __forceinline__ double nn_exact_d2(const double* __restrict__ q, const double* __restrict__ c) {
+    const double ex = q[0] - c[0], ey = q[1] - c[1], ez = q[2] - c[2];
+    return __fma_rn(ez, ez, __fma_rn(ey, ey, __dmul_rn(ex, ex)));
+}
+
 __global__ void __launch_bounds__(256) k_nn_sqdist_pairs(const Brick* __restrict__ A, const int32_t* __restrict__ row_brick,
                                                          const int32_t* __restrict__ qlist, int64_t n_rows,
                                                          const double* __restrict__ meanA,
@@ -394,15 +400,14 @@ __global__ void __launch_bounds__(256) k_nn_sqdist_pairs(const Brick* __restrict
                     const double* qd = meanA + 3 * (size_t)S.row[o];
                     const double* c = meanB + 3 * (size_t)rc.x;
                     const float4* cl = locB + (size_t)rc.x;
-                    float blf = bl < 1e30 ? (float)bl * 1.00002f : 3.0e38f;
+                    float blf = bl < 1e30 ? (float)bl * 1.00004f + 1e-9f : 3.0e38f;
                     for (int i = sub; i < rc.y; i += 4) {
                         const float4 p = __ldg(cl + i);
                         const float fx = sx - p.x, fy = sy - p.y, fz = sz - p.z;
                         const float d2f = fx * fx + fy * fy + fz * fz;
                         if (d2f <= blf) {                       // float32 error ~2e-6 relative: could win -> float64
-                            const double ex = qd[0] - c[3 * i], ey = qd[1] - c[3 * i + 1], ez = qd[2] - c[3 * i + 2];
-                            bl = fmin(bl, ex * ex + ey * ey + ez * ez);
-                            blf = (float)bl * 1.00002f;
+                            bl = fmin(bl, nn_exact_d2(qd, c + 3 * i));
+                            blf = (float)bl * 1.00004f + 1e-9f;
                         }
                     }
                 }
@@ -421,7 +426,7 @@ __global__ void __launch_bounds__(256) k_nn_sqdist_pairs(const Brick* __restrict
             const int src = __ffs(need) - 1;
             need &= need - 1;
             const int64_t rq = S.row[src];
-            const double qx = meanA[3 * rq], qy = meanA[3 * rq + 1], qz = meanA[3 * rq + 2];
+            const double* qdr = meanA + 3 * rq;
             const uint64_t key = A[__shfl_sync(0xFFFFFFFFu, a, src)].key;
             const int bz = (int)key_z(key), by = (int)key_y(key), bx = (int)key_x(key);
             double bq = __shfl_sync(0xFFFFFFFFu, best, src);
@@ -441,11 +446,7 @@ __global__ void __launch_bounds__(256) k_nn_sqdist_pairs(const Brick* __restrict
                         const int id = hash_find(hB, pack_key(0u, (uint32_t)z, (uint32_t)y, (uint32_t)x));
                         if (id < 0) continue;
                         const int cb = B[id].base, cn = B[id].count;
-                        for (int i = 0; i < cn; ++i) {
-                            const double ex = qx - meanB[3 * (size_t)(cb + i)], ey = qy - meanB[3 * (size_t)(cb + i) + 1],
-                                         ez = qz - meanB[3 * (size_t)(cb + i) + 2];
-                            mine = fmin(mine, ex * ex + ey * ey + ez * ez);
-                        }
+                        for (int i = 0; i < cn; ++i) mine = fmin(mine, nn_exact_d2(qdr, meanB + 3 * (size_t)(cb + i)));
                     }
                 }
                 #pragma unroll

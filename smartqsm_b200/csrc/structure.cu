@@ -300,17 +300,18 @@ __global__ void __launch_bounds__(256) k_winner_flags(const int32_t* __restrict_
     flags[e] = f;      // flags[n] = 0 so that the exclusive scan yields the totals at [n]
 }
 
+// one thread per ROW (= voxel): the winner entry of the row is looked up, so the six row arrays are written coalesced and only
+// the reads (winner entry -> point) are scattered (entry-parallel with scattered 45-byte writes: 1.43 ms per C3 thunk)
 __global__ void __launch_bounds__(256) k_rows_fill(const float* __restrict__ P, const float* __restrict__ D,
-                                                   const int32_t* __restrict__ ent_row, const uint32_t* __restrict__ winner,
+                                                   const uint32_t* __restrict__ winner,
                                                    const uint32_t* __restrict__ ent_val, const int64_t* __restrict__ scan,
-                                                   int64_t e0, int64_t n, int64_t out_base, float4* __restrict__ xyz,
+                                                   int64_t e0, int64_t n_rows, int64_t out_base, float4* __restrict__ xyz,
                                                    float4* __restrict__ disp, int32_t* __restrict__ pt_out,
                                                    int32_t* __restrict__ out_pos, int32_t* __restrict__ canon,
                                                    uint8_t* __restrict__ interior) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    int row = ent_row[e];
-    if (row < 0 || winner[row] != (uint32_t)e) return;
+    int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const uint32_t e = winner[row];
     uint32_t v = ent_val[e0 + e];
     uint32_t pt = v & 0x7FFFFFFFu;
     bool inner = (v >> 31) != 0;
@@ -381,7 +382,7 @@ void build_level0(Ctx& cx, const float* d_P, const float* d_D, const TilingResul
     cx.launches++;
     {
         ProfScope ps(cx, "vx_brickmap", (double)n * 14.0 * 2, 0.0);
-        brickmap_build(cx, L0.map, ent_key.p, ent_pos.p, n, ent_brick.p);
+        brickmap_build(cx, L0.map, ent_key.p, ent_pos.p, n, ent_brick.p, n / 16);
     }
     L0.n = L0.map.n_rows;
     SQSM_CHECK(L0.n > 0, "no voxel survived voxelisation");
@@ -400,8 +401,8 @@ void build_level0(Ctx& cx, const float* d_P, const float* d_D, const TilingResul
     rows.out.alloc(n0, st);
     rows.canon.alloc(n0, st);
     rows.interior.alloc(n0, st);
-    k_rows_fill<<<grid, 256, 0, st>>>(d_P, d_D, ent_row.p, winner.p, tl.ent_val.p, scan.p, e0, n, out_base, rows.xyz.p,
-                                      rows.disp.p, rows.pt.p, rows.out.p, rows.canon.p, rows.interior.p);
+    k_rows_fill<<<div_up(n0, 256), 256, 0, st>>>(d_P, d_D, winner.p, tl.ent_val.p, scan.p, e0, n0, out_base, rows.xyz.p,
+                                                 rows.disp.p, rows.pt.p, rows.out.p, rows.canon.p, rows.interior.p);
     cx.launches++;
     int64_t tot = 0;
     SQSM_CUDA(cudaMemcpyAsync(&tot, scan.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -425,12 +426,25 @@ void build_level0(Ctx& cx, const float* d_P, const float* d_D, const TilingResul
 
 // nbr[k][o] = row of the active voxel at coords(o) + (kz-1, ky-1, kx-1), k = kz*9+ky*3+kx, else -1.
 // "Clean bounds" rule: output rows outside [0, spatial_shape) keep the centre only.
+// DENSE: the [27][n] table (-1 = absent).  CSR: a 27-bit presence mask, an offset and the present rows only, in ascending
+// kernel offset - 30 instead of 108 bytes per row at level 0, where 5 of the 27 neighbours exist and every convolution
+// of the level re-reads the table from HBM.  The space of a block's rows is reserved with one atomicAdd per block (a block's
+// rows are contiguous in the list; the order of the blocks in it varies from run to run, the content of a row does not).
+template <bool DENSE, bool CSR>
 __global__ void __launch_bounds__(256) k_subm_nbr(const Brick* __restrict__ bricks, const int32_t* __restrict__ bnbr,
                                                   const int32_t* __restrict__ row_brick, const uint16_t* __restrict__ row_pos,
                                                   int64_t n, const int32_t* __restrict__ shape, int batch_size, int batch0,
-                                                  int32_t* __restrict__ nbr, unsigned long long* __restrict__ stats) {
+                                                  int32_t* __restrict__ nbr, uint32_t* __restrict__ c_mask,
+                                                  uint32_t* __restrict__ c_off, int32_t* __restrict__ c_list,
+                                                  unsigned long long* __restrict__ stats) {
     int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int pairs = 0, far = 0;
+    int rr[CSR ? 27 : 1];
+    if (CSR) {
+        #pragma unroll
+        for (int k = 0; k < 27; ++k) rr[k] = -1;
+    }
+    uint32_t mask = 0;
     if (o < n) {
         int b = row_brick[o];
         uint32_t pos = row_pos[o];
@@ -461,37 +475,84 @@ __global__ void __launch_bounds__(256) k_subm_nbr(const Brick* __restrict__ bric
                         int nbid = nb[bz * 9 + by * 3 + bx];
                         if (nbid >= 0) r = brick_row(&bricks[nbid], pos_of(zz & 7, yy & 7, xx & 7));
                     }
-                    nbr[(size_t)k * n + o] = r;
+                    if (DENSE) nbr[(size_t)k * n + o] = r;
+                    if (CSR) { rr[k] = r; mask |= (r >= 0 ? 1u : 0u) << k; }
                     pairs += (r >= 0);
                 }
             }
         }
     }
-    // block-level tally of active pairs / far-face rows
-    pairs = __reduce_add_sync(0xFFFFFFFFu, pairs);
+    // block-level tally of active pairs / far-face rows (one atomic per block: the counters share a cache line); the CSR
+    // form reserves the block's run of the list with the same atomic
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    __shared__ int s_wtot[8], s_wfar[8];
+    __shared__ unsigned long long s_base;
+    int incl = pairs;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
     far = __reduce_add_sync(0xFFFFFFFFu, far);
-    if ((threadIdx.x & 31) == 0 && (pairs | far)) {
-        atomicAdd(&stats[0], (unsigned long long)pairs);
-        if (far) atomicAdd(&stats[1], (unsigned long long)far);
+    if (lane == 0) { s_wtot[wp] = total; s_wfar[wp] = far; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0, f = 0;
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) { const int v = s_wtot[i]; s_wtot[i] = run; run += v; f += s_wfar[i]; }
+        s_base = run ? atomicAdd(&stats[0], (unsigned long long)run) : 0ull;
+        if (f) atomicAdd(&stats[1], (unsigned long long)f);
+    }
+    __syncthreads();
+    if (CSR) {
+        const unsigned long long base = s_base + (unsigned long long)s_wtot[wp];
+        // the warp's entries are staged in shared memory and leave as one contiguous, coalesced run
+        __shared__ int32_t s_list[8][27 * 32];
+        int32_t* sl = s_list[wp];
+        int w_off = incl - pairs;
+        if (o < n) {
+            c_mask[o] = mask;
+            c_off[o] = (uint32_t)base + (uint32_t)w_off;
+        }
+        #pragma unroll
+        for (int k = 0; k < 27; ++k)
+            if (rr[k] >= 0) sl[w_off++] = rr[k];
+        __syncwarp();
+        for (int j = lane; j < total; j += 32) c_list[base + j] = sl[j];
     }
 }
 
-void build_subm(Ctx& cx, LevelTables& L, int batch0, int n_batches, int batch_size, int64_t* far_face) {
+void build_subm(Ctx& cx, LevelTables& L, int batch0, int n_batches, int batch_size, int64_t* far_face, bool want_dense,
+                bool want_csr) {
     cudaStream_t st = cx.st;
     (void)n_batches;
     if (L.n == 0) return;
+    SQSM_CHECK(want_dense || want_csr, "build_subm: no table requested");
     brickmap_build_neighbours(cx, L.map);
-    L.nbr.alloc(27 * L.n, st);
-    ProfScope ps(cx, "rb_subm_nbr", (double)L.n * (27.0 * 4 + 6.0), 0.0);
+    if (want_dense) L.nbr.alloc(27 * L.n, st);
+    if (want_csr) {
+        SQSM_CHECK(27 * L.n < (1ll << 32), "level too large for 32-bit rulebook offsets (lower SQSM_MAX_ENTRIES_PER_PASS)");
+        L.nbr_mask.alloc(L.n, st);
+        L.nbr_off.alloc(L.n, st);
+        L.nbr_list.alloc(27 * L.n, st);      // upper bound; only the first `pairs` entries are ever touched
+    }
+    ProfScope ps(cx, "rb_subm_nbr", (double)L.n * ((want_dense ? 27.0 * 4 : 0.0) + (want_csr ? 8.0 : 0.0) + 6.0), 0.0);
     DBuf<unsigned long long> stats(2, st);
     stats.zero();
-    k_subm_nbr<<<div_up(L.n, 256), 256, 0, st>>>(L.map.bricks.p, L.map.bnbr.p, L.row_brick.p, L.row_pos.p, L.n,
-                                                 L.shape.p, batch_size, batch0, L.nbr.p, stats.p);
+    const int grid = div_up(L.n, 256);
+#define SQSM_SUBM(D_, C_) k_subm_nbr<D_, C_><<<grid, 256, 0, st>>>(L.map.bricks.p, L.map.bnbr.p, L.row_brick.p, L.row_pos.p, L.n, \
+        L.shape.p, batch_size, batch0, L.nbr.p, L.nbr_mask.p, L.nbr_off.p, L.nbr_list.p, stats.p)
+    if (want_dense && want_csr) SQSM_SUBM(true, true);
+    else if (want_csr) SQSM_SUBM(false, true);
+    else SQSM_SUBM(true, false);
+#undef SQSM_SUBM
     cx.launches++;
     unsigned long long hs[2];
     SQSM_CUDA(cudaMemcpyAsync(hs, stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
     SQSM_CUDA(cudaStreamSynchronize(st));
     L.pairs = (int64_t)hs[0];
+    if (want_csr) ps.r.bytes += 4.0 * (double)L.pairs;
     if (far_face) *far_face = (int64_t)hs[1];
 }
 
@@ -585,7 +646,7 @@ bool build_down(Ctx& cx, LevelTables& L, LevelTables& Ln, int batch0, int n_batc
     cx.launches++;
     {
         ProfScope ps(cx, "rb_brickmap", (double)n * 14.0 * 2, 0.0);
-        brickmap_build(cx, Ln.map, ent_key.p, ent_pos.p, n, ent_brick.p);
+        brickmap_build(cx, Ln.map, ent_key.p, ent_pos.p, n, ent_brick.p, std::max<int64_t>(L.map.n_bricks / 4, 1024));
     }
     Ln.n = Ln.map.n_rows;
     L.parent.alloc(n, st);

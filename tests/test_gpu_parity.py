@@ -311,6 +311,53 @@ def test_chamfer_voxel_counts_and_sums(leafoff_state, n, seed):
     assert abs(sums[0] - s0) <= 1e-12 * s0 and abs(sums[1] - s1) <= 1e-12 * s1
 
 
+def _chamfer_sums_of(eng, P, Q):
+    """Partial Chamfer sums of two arbitrary clouds through the sharded-step calls (state = P, candidate = Q)."""
+    eng.set_state(P.astype(np.float32), np.zeros_like(P, dtype=np.float32))
+    dq = torch.from_numpy(np.ascontiguousarray(Q.astype(np.float32))).cuda()
+    dd = torch.zeros_like(dq)
+    eng.step_set_candidate(dq.data_ptr(), dd.data_ptr(), len(Q))
+    torch.cuda.synchronize()
+    return eng.step_chamfer(0, 1)
+
+
+@pytest.mark.parametrize("case", ["tree", "lattice_ties", "far_apart", "dense_bricks"])
+def test_chamfer_nn_search_exact(leafoff_state, case):
+    """The 1-NN search of the monitor on arbitrary cloud pairs, against cKDTree on the voxel means (sums to rounding, two runs
+    bit-identical).  Cases: a tree and a jittered subset; exact lattice points (every query has several nearest neighbours at
+    EXACTLY the same distance: the float32 screening cannot rank them); clouds more than a brick apart (ring search for every
+    query); bricks with several hundred voxels."""
+    from scipy.spatial import cKDTree
+    from smartqsm_b200.synthetic import make_tree
+    rng = np.random.default_rng(11)
+    if case == "tree":
+        P = make_tree(60000, 5).astype(np.float32)
+        Q = (P[rng.permutation(len(P))[:50000]] + rng.normal(0, 0.02, (50000, 3))).astype(np.float32)
+    elif case == "lattice_ties":
+        g = np.stack(np.meshgrid(*[np.arange(24)] * 3, indexing="ij"), -1).reshape(-1, 3)
+        P = (g * 0.03125).astype(np.float32)                              # exact in binary: ties are exact ties
+        Q = (g[(g.sum(1) % 2) == 0] * 0.03125 + 0.015625).astype(np.float32)
+    elif case == "far_apart":
+        P = rng.uniform(0, 0.5, (3000, 3)).astype(np.float32)
+        Q = (rng.uniform(0, 0.5, (2500, 3)) + np.array([0.9, 0.3, 0.0])).astype(np.float32)
+    else:
+        P = rng.uniform(0, 0.4, (200000, 3)).astype(np.float32)
+        Q = rng.uniform(0, 0.4, (150000, 3)).astype(np.float32)
+    res = []
+    for _ in range(2):
+        eng = make_engine(leafoff_state, monitored_by_chamfer_distance=True)
+        res.append(_chamfer_sums_of(eng, P, Q))
+    assert res[0] == res[1]                                               # bit-identical float64 sums and counts
+    P64, Q64 = P.astype(np.float64), Q.astype(np.float64)
+    mn = np.minimum(P64.min(0), Q64.min(0))
+    Pv, _ = OC.voxel_trace(P64, 0.01, mn)
+    Qv, _ = OC.voxel_trace(Q64, 0.01, mn)
+    assert res[0][1] == [len(Pv), len(Qv)]
+    s0 = float(np.sum(cKDTree(Qv).query(Pv, k=1)[0] ** 2))
+    s1 = float(np.sum(cKDTree(Pv).query(Qv, k=1)[0] ** 2))
+    assert abs(res[0][0][0] - s0) <= 1e-12 * s0 and abs(res[0][0][1] - s1) <= 1e-12 * s1
+
+
 def test_radius_graph_points_and_boundaries():
     """Closed ball in float64 (SciPy semantics) including exact-boundary pairs."""
     from smartqsm_b200._lib import Engine
@@ -625,3 +672,28 @@ def test_sparse_loop_kernel_against_dense_paths(leafoff_state, small_tree, monke
     assert outs[0][3][0] == outs[1][3][0] and np.allclose(outs[0][3], outs[1][3], rtol=1e-3)
     assert np.allclose(outs[0][4], outs[1][4], rtol=1e-3)
     assert np.abs(outs[0][0] - outs[1][0]).max() < 1e-4 and np.abs(outs[0][1] - outs[1][1]).max() < 1e-4
+
+
+def test_compact_level0_rulebook_is_bit_identical(leafoff_state, small_tree, monkeypatch):
+    """Level 0 reads its SubM rulebook in the compact form (presence mask + offset + present rows, k_subm_nbr<.., CSR>);
+    SQSM_NO_CSR=1 restores the dense [27][n] table.  The sparse-loop kernel accumulates the same neighbours in the same
+    order either way: the states must be bit-identical (and both agree with the oracle: check_iteration runs with the
+    debug capture on, which builds BOTH tables, compares the dense one with the oracle's rulebook and lets the
+    convolutions read the compact one)."""
+    from smartqsm_b200.synthetic import make_tree
+    pts = make_tree(150000, 14, True)
+    outs = []
+    for no_csr in (False, True):
+        if no_csr:
+            monkeypatch.setenv("SQSM_NO_CSR", "1")
+        else:
+            monkeypatch.delenv("SQSM_NO_CSR", raising=False)
+        check_iteration(leafoff_state, small_tree)
+        eng = make_engine(leafoff_state, monitored_by_chamfer_distance=True)
+        eng.set_points(pts)
+        stats = [eng.contract_step() for _ in range(3)]
+        P, D = eng.result()
+        outs.append((P, D, [(s["n_out"], s["accepted"], s["chamfer"], s["pairs_l0"]) for s in stats]))
+    monkeypatch.delenv("SQSM_NO_CSR", raising=False)
+    assert outs[0][2] == outs[1][2]
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
