@@ -250,6 +250,25 @@ def tree_tail(eng, fetch_host: bool, host_out=None):
     return 0, (m, e)
 
 
+def tree_tail_sharded(eng, rank: int, world: int, fetch_host: bool, host_out=None):
+    """C5: every rank holds the final state; the skeletal sample is repeated everywhere (2 ms) and the radius-neighbour
+    edge list is produced in node ranges, one per rank (``sqsm_radius_graph_range``: the whole list is the concatenation in
+    rank order).  Rank 0 copies the state and the sample out, every rank its slice of the edges."""
+    m = eng.skeletal_sample(SKELETAL_VOXEL, fetch=False)
+    lo, hi = (m * rank) // world, (m * (rank + 1)) // world
+    if fetch_host:
+        b = 0
+        if rank == 0:
+            n = eng.result_into(host_out["P"].data_ptr(), host_out["D"].data_ptr())
+            eng.skeletal_sample_into(SKELETAL_VOXEL, host_out["ids"].data_ptr(), host_out["sk"].data_ptr(), host_out["rad"].data_ptr())
+            b = n * 24 + m * (8 + 12 + 4)
+        cap = host_out["edges"].numel() * host_out["edges"].element_size() // 16
+        e = eng.radius_graph_range(EDGE_R, lo, hi, host_out["edges"].data_ptr(), cap)
+        return b + e * 16, (m if rank == 0 else 0, e)
+    e = eng.radius_graph_range_count(EDGE_R, lo, hi)              # device-resident leg: the slice stays in HBM
+    return 0, (m if rank == 0 else 0, e)
+
+
 class TreeJob:
     """C1-C4: this rank's trees, one after the other on one engine (the reference's file loop, smartqsm.py:837)."""
 
@@ -298,7 +317,7 @@ class ShardedJob:
         drv = ShardedTreeContraction(eng, self.rank, self.world, self.device, monitored=eng_monitored(eng))
         stats = [drv.contract() for _ in range(CFG["max_iteration"])]
         self.exchange_bytes = drv.exchange_bytes
-        d2h, sz = (tree_tail(eng, e2e, host_out) if self.rank == 0 else (0, (0, 0)))   # the result is needed once
+        d2h, sz = tree_tail_sharded(eng, self.rank, self.world, e2e, host_out)
         return stats, d2h, [sz]
 
 
@@ -427,6 +446,7 @@ def main_b200(args):
     prof = eng.profile_all()
     eng.profile_enable(False)
     total_pts = allsum(float(job.points))
+    edges_total = int(allsum(float(sum(s[1] for s in sizes))))     # C5: every rank holds one slice of the edge list
 
     if args.device_only:
         dev_ms_max = allmax(dev_ms)
@@ -562,7 +582,9 @@ def main_b200(args):
             line["result_digest"] = digest
             line["exchange"] = {"collective": "all_gather_into_tensor (NCCL), once per thunk, on the engine's stream",
                                 "bytes_per_thunk_per_rank": job.exchange_bytes,
-                                "replicated_per_rank": "tiling, Chamfer voxel means; skeletal sampling + radius graph on rank 0 only"}
+                                "edges_total": edges_total,
+                                "replicated_per_rank": "tiling, Chamfer voxel means, skeletal sampling; the radius graph is "
+                                                       "produced in node ranges, one per rank (sqsm_radius_graph_range)"}
         if not args.no_cpu_baseline:
             import torch as _t
             from smartqsm_b200.synthetic import make_tree

@@ -129,6 +129,12 @@ int  sqsm_skeletal_sample(sqsm_handle h, double voxel, int64_t* m,
  * (float64 test), lexicographic.  Call with h_edges == NULL to obtain *n_edges only. */
 int  sqsm_radius_graph(sqsm_handle h, double r, int64_t* n_edges, int64_t* h_edges_ij);
 
+/* The part of that edge list whose first node lies in [node_lo, node_hi): the list of the whole sample is the
+ * concatenation over consecutive node ranges, so the ranks of a sharded tree (configuration C5) each produce and copy
+ * out one slice.  `capacity` = pairs that fit h_edges_ij (< 0: unchecked).  Not cached. */
+int  sqsm_radius_graph_range(sqsm_handle h, double r, int64_t node_lo, int64_t node_hi, int64_t* n_edges,
+                             int64_t* h_edges_ij, int64_t capacity);
+
 /* Same operator on caller-provided points (host float32 M x 3), independent of the state. */
 int  sqsm_radius_graph_points(sqsm_handle h, const float* h_points_xyz, int64_t m, double r,
                               int64_t* n_edges, int64_t* h_edges_ij, int64_t capacity);

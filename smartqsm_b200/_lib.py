@@ -67,7 +67,7 @@ EXPORTS = [
     "sqsm_finalize_weights", "sqsm_set_points_f64", "sqsm_set_points_dev_f32", "sqsm_set_state_f32", "sqsm_contract_step",
     "sqsm_step_begin", "sqsm_step_segment", "sqsm_step_set_candidate", "sqsm_step_chamfer", "sqsm_step_finish",
     "sqsm_result_size", "sqsm_get_result", "sqsm_skeletal_sample", "sqsm_radius_graph",
-    "sqsm_radius_graph_points", "sqsm_debug_capture", "sqsm_debug_level_size", "sqsm_debug_voxels",
+    "sqsm_radius_graph_points", "sqsm_radius_graph_range", "sqsm_debug_capture", "sqsm_debug_level_size", "sqsm_debug_voxels",
     "sqsm_debug_batch_shapes", "sqsm_debug_level_tables", "sqsm_debug_canon_to_internal",
     "sqsm_debug_predictions", "sqsm_debug_features", "sqsm_profile_reset", "sqsm_profile_get",
     "sqsm_profile_enable", "sqsm_profile_families", "sqsm_timer_start", "sqsm_timer_stop", "sqsm_launch_count",
@@ -112,6 +112,7 @@ def load_library() -> C.CDLL:
         "sqsm_skeletal_sample": ([vp, f64, P(i64), vp, vp, vp], C.c_int),
         "sqsm_radius_graph": ([vp, f64, P(i64), vp], C.c_int),
         "sqsm_radius_graph_points": ([vp, vp, i64, f64, P(i64), vp, i64], C.c_int),
+        "sqsm_radius_graph_range": ([vp, f64, i64, i64, P(i64), vp, i64], C.c_int),
         "sqsm_debug_capture": ([vp, i32], C.c_int),
         "sqsm_debug_level_size": ([vp, i32, P(i64)], C.c_int),
         "sqsm_debug_voxels": ([vp, vp, vp, vp], C.c_int),
@@ -328,6 +329,27 @@ class Engine:
         """Copy the edge list into a caller-provided host buffer of at least 16 * E bytes; returns E."""
         e = C.c_int64()
         self._check(self._lib.sqsm_radius_graph(self._h, r, C.byref(e), C.c_void_p(edges_ptr)), "radius_graph")
+        return e.value
+
+    def radius_graph_range(self, r: float, node_lo: int, node_hi: int, edges_ptr: int = 0, capacity: int = -1):
+        """The slice of the edge list whose first node lies in [node_lo, node_hi) (one rank's share of a sharded tree).
+        ``edges_ptr`` = 0 returns the slice as an array; otherwise it is copied into that host buffer and E is returned."""
+        e = C.c_int64()
+        if edges_ptr:
+            self._check(self._lib.sqsm_radius_graph_range(self._h, r, node_lo, node_hi, C.byref(e), C.c_void_p(edges_ptr),
+                                                          capacity), "radius_graph_range")
+            return e.value
+        self._check(self._lib.sqsm_radius_graph_range(self._h, r, node_lo, node_hi, C.byref(e), None, -1), "radius_graph_range")
+        out = np.empty((e.value, 2), np.int64)
+        if e.value:
+            self._check(self._lib.sqsm_radius_graph_range(self._h, r, node_lo, node_hi, C.byref(e), _ptr(out), e.value),
+                        "radius_graph_range")
+        return out
+
+    def radius_graph_range_count(self, r: float, node_lo: int, node_hi: int) -> int:
+        """Build the slice on the device and return its length only (nothing is copied out)."""
+        e = C.c_int64()
+        self._check(self._lib.sqsm_radius_graph_range(self._h, r, node_lo, node_hi, C.byref(e), None, -1), "radius_graph_range")
         return e.value
 
     def radius_graph_points(self, pts: np.ndarray, r: float) -> np.ndarray:

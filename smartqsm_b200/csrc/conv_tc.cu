@@ -502,7 +502,13 @@ std::vector<float> make_tc_weight_image_f16(const float* w_kcico, int kv, int ci
 
 template <int CI, int CO, int KV, bool CAT, bool UP>
 static void launch_tc(Ctx& cx, const TcArgs& a0, bool precise, bool f16) {
-    constexpr int GR = ((CAT ? CI / 2 : CI) == 16 && KV == 27) ? 3 : 2;      // FP16 kernels only (the default path)
+#ifndef SQSM_GR_NARROW
+#define SQSM_GR_NARROW 3
+#endif
+#ifndef SQSM_GR_WIDE
+#define SQSM_GR_WIDE 3
+#endif
+    constexpr int GR = ((CAT ? CI / 2 : CI) == 16 && KV == 27) ? SQSM_GR_NARROW : SQSM_GR_WIDE;      // FP16 kernels only (the default path)
     TcArgs a = a0;
     if (a.n_out <= 0) return;
     a.n_tiles = div_up(a.n_out, 128);

@@ -654,6 +654,26 @@ extern "C" int sqsm_radius_graph(sqsm_handle h, double r, int64_t* n_edges, int6
     SQSM_API_END(h)
 }
 
+extern "C" int sqsm_radius_graph_range(sqsm_handle h, double r, int64_t node_lo, int64_t node_hi, int64_t* n_edges,
+                                      int64_t* out, int64_t capacity) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(h->sk_valid && n_edges, "call sqsm_skeletal_sample first");
+    SQSM_CHECK(node_lo >= 0 && node_lo <= node_hi && node_hi <= h->sk.m, "bad node range");
+    DBuf<int64_t> edges;
+    int64_t E = 0;
+    {
+        ProfScope ps(h->cx, "radius_graph", (double)h->sk.m * 12.0, 0.0);
+        radius_graph(h->cx, h->sk.pts.p, h->sk.m, r, edges, &E, node_lo, node_hi);
+    }
+    *n_edges = E;
+    if (out && E > 0) {
+        SQSM_CHECK(capacity < 0 || E <= capacity, "edge buffer too small");
+        SQSM_CUDA(cudaMemcpyAsync(out, edges.p, sizeof(int64_t) * 2 * E, cudaMemcpyDeviceToHost, h->cx.st));
+    }
+    SQSM_CUDA(cudaStreamSynchronize(h->cx.st));
+    SQSM_API_END(h)
+}
+
 extern "C" int sqsm_radius_graph_points(sqsm_handle h, const float* pts, int64_t m, double r, int64_t* n_edges,
                                         int64_t* out, int64_t capacity) {
     SQSM_API_BEGIN(h)

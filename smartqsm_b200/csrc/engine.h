@@ -141,7 +141,8 @@ struct SkeletalResult {
     int64_t m = 0;
 };
 void skeletal_sample(Ctx& cx, const float* d_P, const float* d_D, int64_t n, double voxel, SkeletalResult& out);
-void radius_graph(Ctx& cx, const float* d_pts, int64_t m, double r, DBuf<int64_t>& edges, int64_t* n_edges);
+void radius_graph(Ctx& cx, const float* d_pts, int64_t m, double r, DBuf<int64_t>& edges, int64_t* n_edges,
+                  int64_t node_lo = 0, int64_t node_hi = -1);
 
 // graph.cu (row a16 / f1: core/skeletonization_pipeline_base.py:75-238)
 struct GraphState {

@@ -707,7 +707,10 @@ __global__ void __launch_bounds__(256) k_radius_pairs(const float* __restrict__ 
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const uint32_t i = order[s];
-    if (MODE == 1 && (i < i_lo || i >= i_hi)) return;
+    if (i < i_lo || i >= i_hi) {                         // MODE 0: node range of this call (a rank's share), MODE 1: chunk
+        if (MODE == 0) cnt[i] = 0;
+        return;
+    }
     const int cell = (int)cell_of[s];
     const double x = (double)P[3 * (size_t)i], y = (double)P[3 * (size_t)i + 1], z = (double)P[3 * (size_t)i + 2];
     int c = 0;
@@ -762,7 +765,12 @@ __global__ void __launch_bounds__(256) k_i32_to_i64(const int32_t* __restrict__ 
     if (i < n) b[i] = (int64_t)a[i];
 }
 
-void radius_graph(Ctx& cx, const float* d_pts, int64_t m, double r, DBuf<int64_t>& edges, int64_t* n_edges) {
+// node_lo / node_hi (default: all nodes): only the edges (i, j) with node_lo <= i < node_hi are produced - the list of the
+// whole cloud is the concatenation of the lists of consecutive node ranges, so ranks can share the work of one cloud
+void radius_graph(Ctx& cx, const float* d_pts, int64_t m, double r, DBuf<int64_t>& edges, int64_t* n_edges, int64_t node_lo,
+                  int64_t node_hi) {
+    if (node_hi < 0 || node_hi > m) node_hi = m;
+    node_lo = std::max<int64_t>(0, std::min(node_lo, node_hi));
     cudaStream_t st = cx.st;
     *n_edges = 0;
     if (m <= 1) return;
@@ -807,7 +815,7 @@ void radius_graph(Ctx& cx, const float* d_pts, int64_t m, double r, DBuf<int64_t
     SQSM_CUDA(cudaMemsetAsync(cnt.p + m, 0, sizeof(int32_t), st));
     const double r2 = r * r;
     k_radius_pairs<0><<<div_up(m, 256), 256, 0, st>>>(d_pts, order.p, cell_sorted.p, m, map.bnbr.p, cstart.p, r2, cnt.p,
-                                                      nullptr, 0u, 0u, nullptr, nullptr);
+                                                      nullptr, (uint32_t)node_lo, (uint32_t)node_hi, nullptr, nullptr);
     DBuf<int64_t> cnt64(m + 1, st), off(m + 1, st);
     k_i32_to_i64<<<div_up(m + 1, 256), 256, 0, st>>>(cnt.p, cnt64.p, m + 1);
     cx.launches += 2;
@@ -862,7 +870,8 @@ void radius_graph(Ctx& cx, const float* d_pts, int64_t m, double r, DBuf<int64_t
         SQSM_CHECK(ne < (1ll << 31), "radius graph: one node range holds more than 2^31 edges (lower SQSM_EDGE_CHUNK)");
         DBuf<uint32_t> ebuf_i(ne, st), ebuf_j(ne, st), ebuf_s(ne, st);
         k_radius_pairs<1><<<div_up(m, 256), 256, 0, st>>>(d_pts, order.p, cell_sorted.p, m, map.bnbr.p, cstart.p, r2, nullptr,
-                                                          off.p, (uint32_t)i0, (uint32_t)i1, ebuf_i.p, ebuf_j.p);
+                                                          off.p, (uint32_t)std::max(i0, node_lo), (uint32_t)std::min(i1, node_hi),
+                                                          ebuf_i.p, ebuf_j.p);   // (nodes outside the range own no edges)
         segmented_sort_u32(cx, ebuf_j.p, ebuf_s.p, ne, i1 - i0, off.p + i0, e0);
         ebuf_j.release();
         k_edges_expand<<<div_up(ne, 256), 256, 0, st>>>(ebuf_i.p, ebuf_s.p, ne, reinterpret_cast<longlong2*>(edges.p) + e0);

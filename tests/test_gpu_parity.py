@@ -697,3 +697,20 @@ def test_compact_level0_rulebook_is_bit_identical(leafoff_state, small_tree, mon
     monkeypatch.delenv("SQSM_NO_CSR", raising=False)
     assert outs[0][2] == outs[1][2]
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_radius_graph_node_ranges_concatenate(leafoff_state, small_tree):
+    """sqsm_radius_graph_range: the edge lists of consecutive node ranges (one per rank of a sharded tree) concatenate to
+    the list of the whole sample, for even and ragged splits, including empty ranges."""
+    eng = make_engine(leafoff_state)
+    eng.set_points(small_tree)
+    eng.contract_step()
+    ids, sk, rad = eng.skeletal_sample(0.01)
+    full = eng.radius_graph(0.055)
+    assert np.array_equal(full, OC.radius_edges(sk, 0.055))
+    m = len(ids)
+    for cuts in ([0, m], [0, m // 2, m], [0, m // 5, m // 5, (3 * m) // 4, m], [(m * r) // 8 for r in range(9)]):
+        parts = [eng.radius_graph_range(0.055, cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1)]
+        assert all(len(p) == 0 or (p[:, 0].min() >= cuts[i] and p[:, 0].max() < cuts[i + 1]) for i, p in enumerate(parts))
+        assert np.array_equal(np.concatenate(parts), full)
+        assert eng.radius_graph_range_count(0.055, cuts[0], cuts[1]) == len(parts[0])
