@@ -72,17 +72,25 @@ __global__ void __launch_bounds__(256) k_brick_insert(BrickHash h, const uint64_
                                                       int64_t n_ent, uint64_t* __restrict__ list, int list_cap,
                                                       int32_t* __restrict__ counter) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_ent) return;
-    uint64_t key = ent_key[e];
-    if (key == kEmptyKey) return;
-    // consecutive entries often fall in the same brick: let one lane per distinct key probe
-    unsigned peers = __match_any_sync(__activemask(), key);
-    if ((int)(__ffs(peers) - 1) != (int)(threadIdx.x & 31)) return;
-    bool ins;
-    uint32_t slot = hash_insert(h, key, &ins);
-    if (slot == 0xFFFFFFFFu) { counter[1] = 1; return; }            // table too small: the host retries
+    const int lane = threadIdx.x & 31;
+    const uint64_t key = e < n_ent ? ent_key[e] : kEmptyKey;
+    bool ins = false;
+    if (key != kEmptyKey) {
+        // consecutive entries often fall in the same brick: let one lane per distinct key probe
+        unsigned peers = __match_any_sync(__activemask(), key);
+        if ((int)(__ffs(peers) - 1) == lane) {
+            uint32_t slot = hash_insert(h, key, &ins);
+            if (slot == 0xFFFFFFFFu) { counter[1] = 1; ins = false; }      // table too small: the host retries
+        }
+    }
+    // one append-cursor atomic per warp (the cursor is a single address: per-key atomics serialise in L2)
+    const unsigned won = __ballot_sync(0xFFFFFFFFu, ins);
+    if (won == 0) return;
+    int base = 0;
+    if (lane == __ffs(won) - 1) base = atomicAdd(counter, __popc(won));
+    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(won) - 1);
     if (ins) {
-        int idx = atomicAdd(counter, 1);
+        const int idx = base + __popc(won & ((1u << lane) - 1u));
         if (idx < list_cap) list[idx] = key; else counter[1] = 1;
     }
 }

@@ -279,7 +279,10 @@ static void launch_conv(Ctx& cx, ConvArgs a) {
 // broadcasts.  The weight image of an offset is padded to an ODD number of 16-byte chunks (CI*CO/4 + 1), so lanes with
 // different offsets fall into different bank groups and a float4 weight read costs 1-3 wavefronts instead of 8-10.
 // Accumulation order per row = ascending offset, channels inside an offset in order, like k_conv (absent neighbours add
-// exact zeros there): the two kernels are bit-identical.  The epilogue can also write the FP16 hi / lo operands of up to two
+// exact zeros there): the two kernels are bit-identical.  ncu (C3): L1TEX 94-99 % busy - the per-lane weight reads - with 19-21
+// of 32 lanes active.  Measured and dropped (profiles/r02_conv_knobs.md): re-dealing a block's rows to its threads by
+// neighbour count so that the lanes of a warp finish together (8 -> 8: 48.4 -> 52.5 ms per C3 step), and four consecutive
+// rows per thread that share the weight reads of the union of their offsets (163 registers, 12 warps per SM: 73.8 ms).  The epilogue can also write the FP16 hi / lo operands of up to two
 // tensor-core consumers (same arithmetic as k_act_split_f16 / the conv_tc epilogue).
 struct SpOut { __half* hi; __half* lo; const float* alpha; const float* beta; };
 struct SpArgs {
@@ -292,6 +295,49 @@ struct SpArgs {
     const uint32_t* csr_off;
     const int32_t* csr_list;
 };
+
+// Epilogue of 8 output channels [ch, ch + 8) of one row: residual, "did not descend" select, float32 store and the FP16
+// hi / lo operands of up to two tensor-core consumers (same arithmetic as k_act_split_f16 / the conv_tc epilogue).
+__device__ __forceinline__ void sp_epilogue8(const SpArgs& s, int row, int co, int ch, float (&r)[8]) {
+    const ConvArgs& a = s.c;
+    const size_t o = (size_t)row * co;
+    const bool take_src = a.sel_flag && a.sel_flag[row] == 0;
+    if (a.res) {
+        const float4 e0 = *reinterpret_cast<const float4*>(a.res + o + ch), e1 = *reinterpret_cast<const float4*>(a.res + o + ch + 4);
+        r[0] += e0.x; r[1] += e0.y; r[2] += e0.z; r[3] += e0.w; r[4] += e1.x; r[5] += e1.y; r[6] += e1.z; r[7] += e1.w;
+    }
+    if (take_src) {
+        const float4 e0 = *reinterpret_cast<const float4*>(a.sel_src + o + ch), e1 = *reinterpret_cast<const float4*>(a.sel_src + o + ch + 4);
+        r[0] = e0.x; r[1] = e0.y; r[2] = e0.z; r[3] = e0.w; r[4] = e1.x; r[5] = e1.y; r[6] = e1.z; r[7] = e1.w;
+    }
+    if (a.out) {
+        *reinterpret_cast<float4*>(a.out + o + ch) = make_float4(r[0], r[1], r[2], r[3]);
+        *reinterpret_cast<float4*>(a.out + o + ch + 4) = make_float4(r[4], r[5], r[6], r[7]);
+    }
+    #pragma unroll
+    for (int u = 0; u < 2; ++u) {                        // the consumers' BN + ReLU + FP16 hi/lo split
+        if (!s.sp[u].hi) continue;
+        float x[8];
+        float mx = 0.f;
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            x[i] = s.sp[u].alpha ? fmaxf(fmaf(r[i], s.sp[u].alpha[ch + i], s.sp[u].beta[ch + i]), 0.f) : r[i];
+            mx = fmaxf(mx, fabsf(x[i]));
+        }
+        if (!(mx < 3.0e4f)) *s.range_flag = 1;
+        uint32_t hw[4], lw[4];
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+            const float2 f = __half22float2(h);
+            const __half2 l = __floats2half2_rn(x[2 * i] - f.x, x[2 * i + 1] - f.y);
+            hw[i] = *reinterpret_cast<const uint32_t*>(&h);
+            lw[i] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        *reinterpret_cast<uint4*>(s.sp[u].hi + o + ch) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(s.sp[u].lo + o + ch) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+}
 
 template <int CI, int CO, int KV, bool BN, bool CAT, bool UP, bool CSR>
 __global__ void __launch_bounds__(256) k_conv_sp(SpArgs s) {
@@ -411,48 +457,11 @@ __global__ void __launch_bounds__(256) k_conv_sp(SpArgs s) {
         }
     }
     if (row >= a.n_out) continue;
-    const size_t o = (size_t)row * CO;
-    const bool take_src = a.sel_flag && a.sel_flag[row] == 0;
     #pragma unroll
     for (int q = 0; q < CO / 8; ++q) {
         float r[8] = {acc[4 * q].x, acc[4 * q].y, acc[4 * q + 1].x, acc[4 * q + 1].y,
                       acc[4 * q + 2].x, acc[4 * q + 2].y, acc[4 * q + 3].x, acc[4 * q + 3].y};
-        const int ch = 8 * q;
-        if (a.res) {
-            const float4 e0 = *reinterpret_cast<const float4*>(a.res + o + ch), e1 = *reinterpret_cast<const float4*>(a.res + o + ch + 4);
-            r[0] += e0.x; r[1] += e0.y; r[2] += e0.z; r[3] += e0.w; r[4] += e1.x; r[5] += e1.y; r[6] += e1.z; r[7] += e1.w;
-        }
-        if (take_src) {
-            const float4 e0 = *reinterpret_cast<const float4*>(a.sel_src + o + ch), e1 = *reinterpret_cast<const float4*>(a.sel_src + o + ch + 4);
-            r[0] = e0.x; r[1] = e0.y; r[2] = e0.z; r[3] = e0.w; r[4] = e1.x; r[5] = e1.y; r[6] = e1.z; r[7] = e1.w;
-        }
-        if (a.out) {
-            *reinterpret_cast<float4*>(a.out + o + ch) = make_float4(r[0], r[1], r[2], r[3]);
-            *reinterpret_cast<float4*>(a.out + o + ch + 4) = make_float4(r[4], r[5], r[6], r[7]);
-        }
-        #pragma unroll
-        for (int u = 0; u < 2; ++u) {                    // the consumers' BN + ReLU + FP16 hi/lo split (conv_tc.cu epilogue)
-            if (!s.sp[u].hi) continue;
-            float x[8];
-            float mx = 0.f;
-            #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                x[i] = s.sp[u].alpha ? fmaxf(fmaf(r[i], s.sp[u].alpha[ch + i], s.sp[u].beta[ch + i]), 0.f) : r[i];
-                mx = fmaxf(mx, fabsf(x[i]));
-            }
-            if (!(mx < 3.0e4f)) *s.range_flag = 1;
-            uint32_t hw[4], lw[4];
-            #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
-                const float2 f = __half22float2(h);
-                const __half2 l = __floats2half2_rn(x[2 * i] - f.x, x[2 * i + 1] - f.y);
-                hw[i] = *reinterpret_cast<const uint32_t*>(&h);
-                lw[i] = *reinterpret_cast<const uint32_t*>(&l);
-            }
-            *reinterpret_cast<uint4*>(s.sp[u].hi + o + ch) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(s.sp[u].lo + o + ch) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-        }
+        sp_epilogue8(s, row, CO, 8 * q, r);
     }
   }
 }
