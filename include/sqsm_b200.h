@@ -104,7 +104,7 @@ int  sqsm_contract_step(sqsm_handle h, SqsmIterStats* stats);
  *   sqsm_step_begin(h, r, R, stats)            -> stats.n_out = rows of this rank's segment
  *   sqsm_step_segment(h, &n, d_xyz, d_disp)    -> copy the segment to DEVICE buffers (NULL: size only)
  *   sqsm_step_set_candidate(h, d_xyz, d_disp, n)   assembled new cloud, DEVICE pointers
- *   sqsm_step_chamfer(h, r, R, sums[2], counts[2]) partial sums over query bricks b = r (mod R)
+ *   sqsm_step_chamfer(h, r, R, sums[2], counts[2]) partial sums over rank r's share of the query rows
  *   sqsm_step_finish(h, monitored, chamfer, &accepted)   accept / reject like :123-131 */
 int  sqsm_step_begin(sqsm_handle h, int32_t shard, int32_t n_shards, SqsmIterStats* stats);
 int  sqsm_step_segment(sqsm_handle h, int64_t* n, float* d_dst_xyz, float* d_dst_disp);

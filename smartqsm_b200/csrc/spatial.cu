@@ -193,10 +193,11 @@ __global__ void __launch_bounds__(256) k_voxel_mean(const long long* __restrict_
 // For every brick of map A: (first row, count) of the 27 bricks of map B around the same coordinates.
 __global__ void __launch_bounds__(256) k_cross_neighbours(const Brick* __restrict__ A, int nA, BrickHash hB,
                                                           const Brick* __restrict__ B, int2* __restrict__ abn,
-                                                          int32_t* __restrict__ abid) {
+                                                          int32_t* __restrict__ abid, int64_t row_lo, int64_t row_hi) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int a = t >> 5, j = t & 31;
     if (a >= nA) return;
+    if ((int64_t)A[a].base + A[a].count <= row_lo || (int64_t)A[a].base >= row_hi) return;   // no query row of this rank
     int2 r = make_int2(0, 0);
     int id = -1;
     if (j < 27) {
@@ -225,14 +226,14 @@ __global__ void __launch_bounds__(256) k_nn_cells(const Brick* __restrict__ A, c
                                                   const uint16_t* __restrict__ row_pos, const int32_t* __restrict__ list,
                                                   int64_t n, const double* __restrict__ meanA, const int32_t* __restrict__ abid,
                                                   const Brick* __restrict__ B, const double* __restrict__ meanB,
-                                                  const __grid_constant__ GridParams g, int shard, int n_shards,
+                                                  const __grid_constant__ GridParams g, int64_t row_lo, int64_t row_hi,
                                                   double* __restrict__ nn2, int32_t* __restrict__ unsettled,
                                                   int32_t* __restrict__ n_unsettled) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
     const int64_t r = list ? (int64_t)list[idx] : idx;
+    if (r < row_lo || r >= row_hi) return;               // this rank's share of the query rows
     const int a = row_brick[r];
-    if (n_shards > 1 && (a % n_shards) != shard) return;
     const uint32_t pos = row_pos[r];
     const int z = (int)(pos >> 6), y = (int)(pos >> 3) & 7, x = (int)pos & 7;
     const double qx = meanA[3 * r], qy = meanA[3 * r + 1], qz = meanA[3 * r + 2];
@@ -318,8 +319,8 @@ __global__ void __launch_bounds__(256) k_nn_sqdist_pairs(const Brick* __restrict
                                                          const float4* __restrict__ locA, const int2* __restrict__ abn,
                                                          BrickHash hB, const Brick* __restrict__ B,
                                                          const double* __restrict__ meanB, const float4* __restrict__ locB,
-                                                         const __grid_constant__ GridParams g, int max_ring, int shard,
-                                                         int n_shards, double* __restrict__ nn2,
+                                                         const __grid_constant__ GridParams g, int max_ring, int64_t row_lo,
+                                                         int64_t row_hi, double* __restrict__ nn2,
                                                          unsigned long long* __restrict__ n_fallback) {
     // queries = the rows listed in qlist (n_rows entries; unsettled by the cell-ring stages) or all rows 0 .. n_rows-1;
     // the exact squared 1-NN distance of query row r goes to nn2[r]
@@ -333,11 +334,15 @@ __global__ void __launch_bounds__(256) k_nn_sqdist_pairs(const Brick* __restrict
                                         (1u << 4) | (1u << 10) | (1u << 12) | (1u << 14) | (1u << 16) | (1u << 22),
                                         0x07FFFFFFu & ~((1u << 13) | (1u << 4) | (1u << 10) | (1u << 12) | (1u << 14) | (1u << 16) | (1u << 22))};
     unsigned fb = 0;
-    for (int64_t base = ((int64_t)blockIdx.x * 8 + w) * 32; base < n_rows; base += (int64_t)gridDim.x * 256) {
+    // a rank's share of the queries is a contiguous ROW range (full warps; a share by brick id modulo the rank count left
+    // 4 of 32 lanes valid at 8 ranks): without a list the loop walks that range only
+    const int64_t first = qlist ? 0 : (row_lo & ~(int64_t)31);
+    if (!qlist) n_rows = row_hi < n_rows ? row_hi : n_rows;
+    for (int64_t base = first + ((int64_t)blockIdx.x * 8 + w) * 32; base < n_rows; base += (int64_t)gridDim.x * 256) {
         bool valid = base + lane < n_rows;
         const int64_t r = valid ? (qlist ? (int64_t)qlist[base + lane] : base + lane) : 0;
+        if (r < row_lo || r >= row_hi) valid = false;
         const int a = valid ? row_brick[r] : 0;
-        if (n_shards > 1 && (a % n_shards) != shard) valid = false;
         if (!__any_sync(0xFFFFFFFFu, valid)) continue;
         const float4 ql = valid ? locA[r] : make_float4(0.f, 0.f, 0.f, 0.f);
         float gm2[3] = {fmaxf(ql.x - slack, 0.f), fmaxf(ql.y - slack, 0.f), fmaxf(ql.z - slack, 0.f)};
@@ -494,7 +499,7 @@ static void voxel_means(Ctx& cx, const float* d_P, int64_t n, const double mn[3]
 }
 
 // Partial Chamfer sums: the 1-NN squared distances of the voxel means of P to those of Q (sums[0]) and of Q to P
-// (sums[1]) restricted to the query bricks b = shard (mod n_shards); counts = number of voxel means of P and Q.
+// (sums[1]) restricted to this shard's contiguous range of query rows; counts = number of voxel means of P and Q.
 // With n_shards = 1 this is the whole monitor; with several ranks the sums are all-reduced by the caller.
 void chamfer_partial(Ctx& cx, const float* d_P, int64_t np, const float* d_Q, int64_t nq, double voxel, int shard,
                      int n_shards, double sums[2], int64_t counts[2]) {
@@ -522,10 +527,14 @@ void chamfer_partial(Ctx& cx, const float* d_P, int64_t np, const float* d_Q, in
     const int nA = A.gm.map.n_bricks, nB = B.gm.map.n_bricks;
     DBuf<int2> abn((int64_t)nA * 32, st), ban((int64_t)nB * 32, st);
     DBuf<int32_t> abid((int64_t)nA * 32, st), baid((int64_t)nB * 32, st);
+    // a rank's share of the queries: the rows [rows * shard / n_shards, rows * (shard + 1) / n_shards) of each cloud
+    const int64_t rowsA = A.gm.map.n_rows, rowsB = B.gm.map.n_rows;
+    const int64_t a_lo = rowsA * shard / n_shards, a_hi = rowsA * (shard + 1) / n_shards;
+    const int64_t b_lo = rowsB * shard / n_shards, b_hi = rowsB * (shard + 1) / n_shards;
     k_cross_neighbours<<<div_up((int64_t)nA * 32, 256), 256, 0, st>>>(A.gm.map.bricks.p, nA, B.gm.map.view(),
-                                                                      B.gm.map.bricks.p, abn.p, abid.p);
+                                                                      B.gm.map.bricks.p, abn.p, abid.p, a_lo, a_hi);
     k_cross_neighbours<<<div_up((int64_t)nB * 32, 256), 256, 0, st>>>(B.gm.map.bricks.p, nB, A.gm.map.view(),
-                                                                      A.gm.map.bricks.p, ban.p, baid.p);
+                                                                      A.gm.map.bricks.p, ban.p, baid.p, b_lo, b_hi);
     cx.launches += 2;
     // optional cell-ring stages (SQSM_CD_RINGS, e.g. "2,3": cubes of 5^3 then 7^3 voxel cells) in front of the brick-level
     // search, which then only sees what is still unsettled.  Default "0" = brick-level search only: on the C3 tree the ring
@@ -542,6 +551,7 @@ void chamfer_partial(Ctx& cx, const float* d_P, int64_t np, const float* d_Q, in
     int64_t n_left[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     auto direction = [&](VoxelMeans& X, VoxelMeans& Y, const int2* xyn, const int32_t* xyid, int which, double* h_sum) {
         const int64_t rows = X.gm.map.n_rows;
+        const int64_t row_lo = which == 0 ? a_lo : b_lo, row_hi = which == 0 ? a_hi : b_hi;
         DBuf<double> nn2(rows, st);
         nn2.zero();                                              // rows of other shards contribute nothing
         DBuf<int32_t> lst[2];
@@ -555,7 +565,7 @@ void chamfer_partial(Ctx& cx, const float* d_P, int64_t np, const float* d_Q, in
             const int grid = div_up(n_cur, 256);
 #define SQSM_RING(R_)                                                                                                       \
             k_nn_cells<R_><<<grid, 256, 0, st>>>(X.gm.map.bricks.p, X.row_brick.p, X.row_pos.p, cur, n_cur, X.mean.p, xyid,   \
-                                                 Y.gm.map.bricks.p, Y.mean.p, X.gm.g, shard, n_shards, nn2.p, lst[flip].p, cnt.p)
+                                                 Y.gm.map.bricks.p, Y.mean.p, X.gm.g, row_lo, row_hi, nn2.p, lst[flip].p, cnt.p)
             switch (rings[s]) {
                 case 1: SQSM_RING(1); break;
                 case 2: SQSM_RING(2); break;
@@ -573,10 +583,11 @@ void chamfer_partial(Ctx& cx, const float* d_P, int64_t np, const float* d_Q, in
             flip ^= 1;
         }
         if (n_cur > 0) {
-            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(div_up(n_cur, 256), kNumSMs * 16));
+            const int64_t span = cur ? n_cur : std::max<int64_t>(row_hi - row_lo, 1) + 32;
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(div_up(span, 256), kNumSMs * 16));
             k_nn_sqdist_pairs<<<grid, 256, 0, st>>>(X.gm.map.bricks.p, X.row_brick.p, cur, n_cur, X.mean.p, X.loc.p, xyn,
-                                                    Y.gm.map.view(), Y.gm.map.bricks.p, Y.mean.p, Y.loc.p, X.gm.g, max_ring, shard,
-                                                    n_shards, nn2.p, nfb.p + which);
+                                                    Y.gm.map.view(), Y.gm.map.bricks.p, Y.mean.p, Y.loc.p, X.gm.g, max_ring, row_lo,
+                                                    row_hi, nn2.p, nfb.p + which);
             cx.launches++;
         }
         // fixed-shape reduction over the rows in row order: the sum is bit-reproducible
