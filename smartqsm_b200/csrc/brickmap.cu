@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(256) k_brick_insert(BrickHash h, const uint64_
     const uint64_t key = e < n_ent ? ent_key[e] : kEmptyKey;
     bool ins = false;
     if (key != kEmptyKey) {
-        // consecutive entries often fall in the same brick: let one lane per distinct key probe
+        // consecutive entries often fall in the same brick: let one lane per distinct key probe (every lane probing for
+        // itself: 252 instead of 212 us for 8.5 M entries)
         unsigned peers = __match_any_sync(__activemask(), key);
         if ((int)(__ffs(peers) - 1) == lane) {
             uint32_t slot = hash_insert(h, key, &ins);
