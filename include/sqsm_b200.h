@@ -135,6 +135,15 @@ int  sqsm_radius_graph(sqsm_handle h, double r, int64_t* n_edges, int64_t* h_edg
 int  sqsm_radius_graph_range(sqsm_handle h, double r, int64_t node_lo, int64_t node_hi, int64_t* n_edges,
                              int64_t* h_edges_ij, int64_t capacity);
 
+/* Row f3 - the ball occupancy queries of core/refinement.py:448-456
+ * (kdtree.query_ball_point(points[path], r = reference_radii[path] * factor) inside the loop over the paths): the ball of
+ * EVERY node with its own radius in one call, as a CSR (h_offsets: M + 1 entries; h_indices: ascending node indices, the
+ * node itself included; closed ball, float64 d2 <= r * r like cKDTree; a negative radius acts like its magnitude, NaN gives an empty list).
+ * The sequential loop of the reference then only unites precomputed lists.  Call with h_indices == NULL to obtain the
+ * offsets and *n_total, then with a buffer of `capacity` >= *n_total entries. */
+int  sqsm_ball_lists(sqsm_handle h, const float* h_points_xyz, int64_t m, const double* h_radii, int64_t* h_offsets,
+                     int64_t* n_total, int32_t* h_indices, int64_t capacity);
+
 /* Same operator on caller-provided points (host float32 M x 3), independent of the state. */
 int  sqsm_radius_graph_points(sqsm_handle h, const float* h_points_xyz, int64_t m, double r,
                               int64_t* n_edges, int64_t* h_edges_ij, int64_t capacity);

@@ -67,7 +67,7 @@ EXPORTS = [
     "sqsm_finalize_weights", "sqsm_set_points_f64", "sqsm_set_points_dev_f32", "sqsm_set_state_f32", "sqsm_contract_step",
     "sqsm_step_begin", "sqsm_step_segment", "sqsm_step_set_candidate", "sqsm_step_chamfer", "sqsm_step_finish",
     "sqsm_result_size", "sqsm_get_result", "sqsm_skeletal_sample", "sqsm_radius_graph",
-    "sqsm_radius_graph_points", "sqsm_radius_graph_range", "sqsm_debug_capture", "sqsm_debug_level_size", "sqsm_debug_voxels",
+    "sqsm_radius_graph_points", "sqsm_radius_graph_range", "sqsm_ball_lists", "sqsm_debug_capture", "sqsm_debug_level_size", "sqsm_debug_voxels",
     "sqsm_debug_batch_shapes", "sqsm_debug_level_tables", "sqsm_debug_canon_to_internal",
     "sqsm_debug_predictions", "sqsm_debug_features", "sqsm_profile_reset", "sqsm_profile_get",
     "sqsm_profile_enable", "sqsm_profile_families", "sqsm_timer_start", "sqsm_timer_stop", "sqsm_launch_count",
@@ -113,6 +113,7 @@ def load_library() -> C.CDLL:
         "sqsm_radius_graph": ([vp, f64, P(i64), vp], C.c_int),
         "sqsm_radius_graph_points": ([vp, vp, i64, f64, P(i64), vp, i64], C.c_int),
         "sqsm_radius_graph_range": ([vp, f64, i64, i64, P(i64), vp, i64], C.c_int),
+        "sqsm_ball_lists": ([vp, vp, i64, vp, vp, P(i64), vp, i64], C.c_int),
         "sqsm_debug_capture": ([vp, i32], C.c_int),
         "sqsm_debug_level_size": ([vp, i32, P(i64)], C.c_int),
         "sqsm_debug_voxels": ([vp, vp, vp, vp], C.c_int),
@@ -351,6 +352,21 @@ class Engine:
         e = C.c_int64()
         self._check(self._lib.sqsm_radius_graph_range(self._h, r, node_lo, node_hi, C.byref(e), None, -1), "radius_graph_range")
         return e.value
+
+    def ball_lists(self, pts: np.ndarray, radii: np.ndarray):
+        """Row f3: ``cKDTree(pts).query_ball_point(pts, r=radii)`` for every node at once -> (offsets int64[M + 1],
+        indices int32[T]); the ball of node i is ``indices[offsets[i]:offsets[i + 1]]``, ascending."""
+        a = np.ascontiguousarray(pts, dtype=np.float32)
+        r = np.ascontiguousarray(radii, dtype=np.float64)
+        assert a.ndim == 2 and a.shape[1] == 3 and r.shape == (a.shape[0],)
+        off = np.empty(a.shape[0] + 1, np.int64)
+        t = C.c_int64()
+        self._check(self._lib.sqsm_ball_lists(self._h, _ptr(a), a.shape[0], _ptr(r), _ptr(off), C.byref(t), None, 0), "ball_lists")
+        idx = np.empty(t.value, np.int32)
+        if t.value:
+            self._check(self._lib.sqsm_ball_lists(self._h, _ptr(a), a.shape[0], _ptr(r), _ptr(off), C.byref(t), _ptr(idx), t.value),
+                        "ball_lists")
+        return off, idx
 
     def radius_graph_points(self, pts: np.ndarray, r: float) -> np.ndarray:
         a = np.ascontiguousarray(pts, dtype=np.float32)

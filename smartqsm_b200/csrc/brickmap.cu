@@ -75,7 +75,10 @@ __global__ void __launch_bounds__(256) k_brick_insert(BrickHash h, const uint64_
     const int lane = threadIdx.x & 31;
     const uint64_t key = e < n_ent ? ent_key[e] : kEmptyKey;
     bool ins = false;
-    if (key != kEmptyKey) {
+    // once the table is known to be too small the host retries with a larger one: do not keep probing a full table (every
+    // probe sequence would walk all of it)
+    const bool overflowed = *reinterpret_cast<volatile int32_t*>(counter + 1) != 0;
+    if (key != kEmptyKey && !overflowed) {
         // consecutive entries often fall in the same brick: let one lane per distinct key probe (every lane probing for
         // itself: 252 instead of 212 us for 8.5 M entries)
         unsigned peers = __match_any_sync(__activemask(), key);

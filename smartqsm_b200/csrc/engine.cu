@@ -684,6 +684,41 @@ extern "C" int sqsm_radius_graph_points(sqsm_handle h, const float* pts, int64_t
     SQSM_API_END(h)
 }
 
+// ---- refinement's ball occupancy queries (row f3)
+extern "C" int sqsm_ball_lists(sqsm_handle h, const float* pts, int64_t m, const double* radii, int64_t* offsets,
+                               int64_t* n_total, int32_t* indices, int64_t capacity) {
+    SQSM_API_BEGIN(h)
+    SQSM_CHECK(pts && radii && offsets && n_total && m > 0, "bad arguments");
+    cudaStream_t st = h->cx.st;
+    DBuf<float> d_pts(m * 3, st);
+    DBuf<double> d_rad(m, st);
+    SQSM_CUDA(cudaMemcpyAsync(d_pts.p, pts, sizeof(float) * 3 * m, cudaMemcpyHostToDevice, st));
+    SQSM_CUDA(cudaMemcpyAsync(d_rad.p, radii, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+    // finest grid: cell edge = the mean of the finite positive radii; coarsest: an eighth of the largest finite radius
+    double finest = 0, largest = 0;
+    int64_t nf = 0;
+    for (int64_t i = 0; i < m; ++i) {
+        const double a = std::fabs(radii[i]);
+        if (a > 0 && a < 1e30) { finest += a; ++nf; largest = std::max(largest, a); }
+    }
+    finest = nf ? finest / (double)nf : 0.0;
+    DBuf<int64_t> d_off;
+    DBuf<uint32_t> d_idx;
+    int64_t T = 0;
+    {
+        ProfScope ps(h->cx, "ball_lists", (double)m * 20.0, 0.0);
+        ball_lists(h->cx, d_pts.p, m, d_rad.p, finest, largest, d_off, d_idx, &T);
+    }
+    *n_total = T;
+    SQSM_CUDA(cudaMemcpyAsync(offsets, d_off.p, sizeof(int64_t) * (m + 1), cudaMemcpyDeviceToHost, st));
+    if (indices && T > 0) {
+        SQSM_CHECK(T <= capacity, "index buffer too small (n_total holds the required size)");
+        SQSM_CUDA(cudaMemcpyAsync(indices, d_idx.p, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, st));
+    }
+    SQSM_CUDA(cudaStreamSynchronize(st));
+    SQSM_API_END(h)
+}
+
 // ---- connectivity graph + skeleton extraction (row a16 / f1)
 extern "C" int sqsm_graph_construct(sqsm_handle h, const float* pts, int64_t m, const int32_t* simplices, int64_t n_simplices,
                                     double r, const int64_t* preset_edges, int64_t n_preset, int64_t* n_edges) {

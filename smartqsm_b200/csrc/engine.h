@@ -141,6 +141,9 @@ struct SkeletalResult {
     int64_t m = 0;
 };
 void skeletal_sample(Ctx& cx, const float* d_P, const float* d_D, int64_t n, double voxel, SkeletalResult& out);
+// row f3: the ball of every node with its own radius (cKDTree.query_ball_point semantics), CSR, ascending indices
+void ball_lists(Ctx& cx, const float* d_pts, int64_t m, const double* d_radii, double finest_cell, double largest_radius,
+                DBuf<int64_t>& offsets, DBuf<uint32_t>& indices, int64_t* n_total);
 void radius_graph(Ctx& cx, const float* d_pts, int64_t m, double r, DBuf<int64_t>& edges, int64_t* n_edges,
                   int64_t node_lo = 0, int64_t node_hi = -1);
 

@@ -13,6 +13,8 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <memory>
+#include <vector>
 
 namespace sqsm {
 
@@ -888,6 +890,181 @@ void radius_graph(Ctx& cx, const float* d_pts, int64_t m, double r, DBuf<int64_t
         k_edges_expand<<<div_up(ne, 256), 256, 0, st>>>(ebuf_i.p, ebuf_s.p, ne, reinterpret_cast<longlong2*>(edges.p) + e0);
         cx.launches += 2;
     }
+}
+
+// ---------------------------------------------------------------------------------- variable-radius ball lists (row f3)
+//
+// core/refinement.py:448-456 occupies the skeleton nodes around a path with
+//   kdtree.query_ball_point(points[path], r = reference_radii[path] * factor)  ->  np.unique(np.concatenate(...))
+// inside a sequential loop over the paths.  The radii of ALL nodes are known before that loop, so the device computes the
+// ball of every node once - a radius graph with a per-node radius - and the loop only unites precomputed lists.
+// Semantics of cKDTree.query_ball_point (p = 2): j is in the ball of i when the float64 squared distance is <= r_i * r_i;
+// i itself is always a member (a negative radius acts like its magnitude, NaN gives an empty list).  Ascending node index.
+//
+// Radii span three orders of magnitude (twigs 2 mm, trunk 0.4 m), so ONE cell size does not work: with cells of the mean
+// radius a trunk node would probe 10^6 cells.  The points are binned on up to 8 grids whose cell edge grows by 8x per level,
+// the finest at the mean radius; a query uses the finest grid whose cell edge is at least an eighth of its radius, i.e. at
+// most 19^3 cells (27 or 125 for the bulk of the nodes; finer grids for everybody - a quarter of the radius, 11^3 cells - were
+// measured 7x slower on 400 k nodes: the hash probes dominate).  A WARP serves one query: one hash probe per lane and
+// cell, the points of the 32 cells of a batch are dealt evenly to the lanes.  Count pass, scan, fill pass (positions inside
+// the segment from warp ballots: no atomics, a fixed order), segmented sort of every segment.
+constexpr int kBallLevels = 8;
+struct BallLevel { double voxel; BrickHash h; const int32_t* cstart; const uint32_t* order; int k_max; };
+struct BallGrids { BallLevel lv[kBallLevels]; int n; double mn[3]; };
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_ball_lists(const float* __restrict__ P, int64_t m, const double* __restrict__ radii,
+                                                    const __grid_constant__ BallGrids G, int32_t* __restrict__ cnt,
+                                                    const int64_t* __restrict__ off, uint32_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= m) return;
+    const double x = (double)P[3 * i], y = (double)P[3 * i + 1], z = (double)P[3 * i + 2];
+    // cKDTree compares squared distances with r^2: a negative radius acts like its magnitude, NaN gives an empty list
+    const double r = fabs(radii[i]);
+    const double r2 = r * r;
+    if (!(r >= 0.0)) {
+        if (MODE == 0 && lane == 0) cnt[i] = 0;
+        return;
+    }
+    int lvl = 0;
+    while (lvl + 1 < G.n && 8.0 * G.lv[lvl].voxel < r) ++lvl;
+    const BallLevel& L = G.lv[lvl];
+    const int cx0 = (int)floor((x - G.mn[0]) / L.voxel), cy0 = (int)floor((y - G.mn[1]) / L.voxel), cz0 = (int)floor((z - G.mn[2]) / L.voxel);
+    const int k = (int)fmin(floor(r / L.voxel) + 1.0, (double)L.k_max);     // k_max rings cover the whole grid (r = inf)
+    const int side = 2 * k + 1;
+    const int64_t n_cells = (int64_t)side * side * side;
+    int total = 0;
+    const int64_t base = MODE == 1 ? off[i] : 0;
+    for (int64_t t0 = 0; t0 < n_cells; t0 += 32) {
+        const int64_t t = t0 + lane;
+        int b = 0, e = 0;
+        if (t < n_cells) {
+            const int dz = (int)(t / ((int64_t)side * side)) - k, dy = (int)((t / side) % side) - k, dx = (int)(t % side) - k;
+            const int cz = cz0 + dz, cy = cy0 + dy, cx = cx0 + dx;
+            if (cz >= 0 && cy >= 0 && cx >= 0 && cz < 65536 && cy < 65536 && cx < 65536) {
+                const int id = hash_find(L.h, pack_key(0u, (uint32_t)cz, (uint32_t)cy, (uint32_t)cx));
+                if (id >= 0) { b = L.cstart[id]; e = L.cstart[id + 1]; }
+            }
+        }
+        // the candidates of the 32 cells of this batch are dealt evenly to the lanes (a lane walking its own cell would
+        // make the warp wait for the fullest cell): inclusive prefix of the cell sizes, then candidate c belongs to the
+        // first cell whose prefix exceeds c
+        int incl = e - b;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        const int n_cand = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        for (int c0 = 0; c0 < n_cand; c0 += 32) {
+            const int c = c0 + lane;
+            int cell = 0;
+            #pragma unroll
+            for (int st = 16; st > 0; st >>= 1) {
+                const int v = __shfl_sync(0xFFFFFFFFu, incl, cell + st - 1);
+                if (v <= c) cell += st;
+            }
+            cell = min(cell, 31);
+            const int cb = __shfl_sync(0xFFFFFFFFu, b, cell), ci = __shfl_sync(0xFFFFFFFFu, incl, cell), ce = __shfl_sync(0xFFFFFFFFu, e, cell);
+            bool hit = false;
+            uint32_t j = 0;
+            if (c < n_cand) {
+                j = L.order[cb + (c - (ci - (ce - cb)))];
+                const double dx = x - (double)P[3 * (size_t)j], dy = y - (double)P[3 * (size_t)j + 1], dz = z - (double)P[3 * (size_t)j + 2];
+                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                hit = d2 <= r2;
+            }
+            const unsigned w = __ballot_sync(0xFFFFFFFFu, hit);
+            if (MODE == 1 && hit) out[base + total + __popc(w & ((1u << lane) - 1u))] = j;
+            total += __popc(w);
+        }
+    }
+    if (MODE == 0 && lane == 0) cnt[i] = total;
+}
+
+// finest_cell / largest_radius: cell edge of the finest grid and the largest finite radius (from the caller's host copy)
+void ball_lists(Ctx& cx, const float* d_pts, int64_t m, const double* d_radii, double finest_cell, double largest_radius,
+                DBuf<int64_t>& offsets, DBuf<uint32_t>& indices, int64_t* n_total) {
+    cudaStream_t st = cx.st;
+    *n_total = 0;
+    offsets.alloc(m + 1, st);
+    offsets.zero();
+    if (m <= 0) return;
+    SQSM_CHECK(m < (1ll << 31), "ball lists: at most 2^31 - 1 nodes");
+    double mn[3], mx[3];
+    cloud_bounds(cx, d_pts, m, mn, mx);
+    double ext = 0;
+    for (int a = 0; a < 3; ++a) ext = std::max(ext, mx[a] - mn[a]);
+    struct LevelData { BrickMap map; DBuf<int32_t> cstart; DBuf<uint32_t> order; };
+    std::vector<std::unique_ptr<LevelData>> levels;
+    BallGrids G;
+    std::memset(&G, 0, sizeof(G));
+    for (int a = 0; a < 3; ++a) G.mn[a] = mn[a];
+    double cell = std::max(std::max(finest_cell, 1e-6), ext / 65000.0);
+    for (int l = 0; l < kBallLevels; ++l) {
+        Trace trl(cx, " ball level");
+        const bool last = l == kBallLevels - 1 || 8.0 * cell >= largest_radius;
+        if (last) cell = std::max(cell, 0.125 * largest_radius);
+        GridParams g;
+        for (int a = 0; a < 3; ++a) g.mn[a] = mn[a];
+        g.voxel = cell;
+        auto L = std::make_unique<LevelData>();
+        DBuf<uint64_t> ent_key(m, st);
+        DBuf<uint16_t> ent_pos(m, st);
+        DBuf<int32_t> ent_brick(m, st);
+        DBuf<int32_t> err(1, st);
+        err.zero();
+        k_cell_entries<<<div_up(m, 256), 256, 0, st>>>(d_pts, m, g, ent_key.p, ent_pos.p, err.p);
+        cx.launches++;
+        brickmap_build(cx, L->map, ent_key.p, ent_pos.p, m, ent_brick.p, m);     // fine cells: up to one cell per point
+        int32_t herr = 0;
+        SQSM_CUDA(cudaMemcpyAsync(&herr, err.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        SQSM_CUDA(cudaStreamSynchronize(st));
+        SQSM_CHECK(herr == 0, "ball lists: non-finite coordinates");
+        const int nc = L->map.n_bricks;
+        DBuf<int32_t> ccnt((int64_t)nc + 1, st);
+        L->cstart.alloc((int64_t)nc + 1, st);
+        ccnt.zero();
+        k_cell_count<<<div_up(m, 256), 256, 0, st>>>(ent_brick.p, m, ccnt.p);
+        exclusive_scan_i32(cx, ccnt.p, L->cstart.p, (int64_t)nc + 1);
+        DBuf<uint32_t> iota(m, st), cell_sorted(m, st);
+        L->order.alloc(m, st);
+        k_iota_u32<<<div_up(m, 256), 256, 0, st>>>(iota.p, m);
+        cx.launches += 2;
+        int bits = 1;
+        while ((1ll << bits) < nc) ++bits;
+        sort_pairs_u32(cx, (const uint32_t*)ent_brick.p, cell_sorted.p, iota.p, L->order.p, m, 0, bits);
+        G.lv[l].voxel = cell;
+        G.lv[l].h = L->map.view();
+        G.lv[l].cstart = L->cstart.p;
+        G.lv[l].order = L->order.p;
+        G.lv[l].k_max = (int)std::min(std::ceil(ext / cell) + 1.0, 65536.0);
+        G.n = l + 1;
+        levels.push_back(std::move(L));
+        if (last) break;
+        cell *= 8.0;
+    }
+    DBuf<int32_t> cnt(m + 1, st);
+    SQSM_CUDA(cudaMemsetAsync(cnt.p + m, 0, sizeof(int32_t), st));
+    const int grid = div_up(m * 32, 256);
+    { Trace tr(cx, " ball count"); k_ball_lists<0><<<grid, 256, 0, st>>>(d_pts, m, d_radii, G, cnt.p, nullptr, nullptr); }
+    DBuf<int64_t> cnt64(m + 1, st);
+    k_i32_to_i64<<<div_up(m + 1, 256), 256, 0, st>>>(cnt.p, cnt64.p, m + 1);
+    cx.launches += 2;
+    exclusive_scan_i64(cx, cnt64.p, offsets.p, m + 1);
+    int64_t T = 0;
+    SQSM_CUDA(cudaMemcpyAsync(&T, offsets.p + m, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    SQSM_CUDA(cudaStreamSynchronize(st));
+    *n_total = T;
+    if (T == 0) return;
+    SQSM_CHECK(T < (1ll << 31), "ball lists: more than 2^31 - 1 list entries (split the nodes over several calls)");
+    DBuf<uint32_t> raw(T, st);
+    { Trace tr(cx, " ball fill"); k_ball_lists<1><<<grid, 256, 0, st>>>(d_pts, m, d_radii, G, nullptr, offsets.p, raw.p); }
+    cx.launches++;
+    indices.alloc(T, st);
+    { Trace tr(cx, " ball sort"); segmented_sort_u32(cx, raw.p, indices.p, T, m, offsets.p, 0); }
+    SQSM_CUDA(cudaStreamSynchronize(st));               // the level tables go out of scope
 }
 
 }  // namespace sqsm
