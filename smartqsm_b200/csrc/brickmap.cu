@@ -75,15 +75,14 @@ __global__ void __launch_bounds__(256) k_brick_insert(BrickHash h, const uint64_
     const int lane = threadIdx.x & 31;
     const uint64_t key = e < n_ent ? ent_key[e] : kEmptyKey;
     bool ins = false;
-    // once the table is known to be too small the host retries with a larger one: do not keep probing a full table (every
-    // probe sequence would walk all of it)
-    const bool overflowed = *reinterpret_cast<volatile int32_t*>(counter + 1) != 0;
-    if (key != kEmptyKey && !overflowed) {
+    if (key != kEmptyKey) {
         // consecutive entries often fall in the same brick: let one lane per distinct key probe (every lane probing for
         // itself: 252 instead of 212 us for 8.5 M entries)
         unsigned peers = __match_any_sync(__activemask(), key);
         if ((int)(__ffs(peers) - 1) == lane) {
-            uint32_t slot = hash_insert(h, key, &ins);
+            // (the overflow flag is polled inside long probe sequences only: once the table is known to be too small the
+            // host retries with a larger one, and walking a FULL table costs a whole-table scan per insert)
+            uint32_t slot = hash_insert(h, key, &ins, counter + 1);
             if (slot == 0xFFFFFFFFu) { counter[1] = 1; ins = false; }      // table too small: the host retries
         }
     }

@@ -137,11 +137,15 @@ __device__ __forceinline__ int hash_find(const BrickHash& h, uint64_t key) {
 }
 
 // returns slot; *inserted = true when this thread claimed it
-__device__ __forceinline__ uint32_t hash_insert(const BrickHash& h, uint64_t key, bool* inserted) {
+// `abort_flag` (optional): polled every 64 probes - once the caller knows the table is too small (it retries with a larger
+// one) a probe sequence must not keep walking a full table
+__device__ __forceinline__ uint32_t hash_insert(const BrickHash& h, uint64_t key, bool* inserted,
+                                                const int32_t* abort_flag = nullptr) {
     uint32_t slot = (uint32_t)mix64(key) & h.cap_mask;
     *inserted = false;
     #pragma unroll 1
     for (uint32_t probe = 0; probe <= h.cap_mask; ++probe) {
+        if (abort_flag && (probe & 63u) == 63u && *reinterpret_cast<const volatile int32_t*>(abort_flag) != 0) return 0xFFFFFFFFu;
         uint64_t k = h.keys[slot];
         if (k == key) return slot;
         if (k == kEmptyKey) {
