@@ -714,3 +714,17 @@ def test_radius_graph_node_ranges_concatenate(leafoff_state, small_tree):
         assert all(len(p) == 0 or (p[:, 0].min() >= cuts[i] and p[:, 0].max() < cuts[i + 1]) for i, p in enumerate(parts))
         assert np.array_equal(np.concatenate(parts), full)
         assert eng.radius_graph_range_count(0.055, cuts[0], cuts[1]) == len(parts[0])
+
+
+def test_brick_hash_retry_when_every_point_is_its_own_cell():
+    """BrickMap builds size their hash for far fewer bricks than entries and retry with a 4x table when it passes 50 % load
+    (the insert kernel stops probing a table that is known to be too small).  40 000 points spread so thinly that every point
+    is its own radius-graph cell force that path; the edge set must still equal SciPy's."""
+    from smartqsm_b200._lib import Engine
+    rng = np.random.default_rng(8)
+    pts = rng.uniform(0, 40.0, (40000, 3)).astype(np.float32)
+    pts[1000:2000] = pts[:1000] + rng.normal(0, 0.02, (1000, 3)).astype(np.float32)      # some real neighbours
+    eng = Engine()
+    e_g = eng.radius_graph_points(pts, 0.055)
+    e_o = OC.radius_edges(pts, 0.055)
+    assert len(e_o) > 100 and np.array_equal(e_g, e_o)
